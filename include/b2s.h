@@ -1,0 +1,157 @@
+/*
+ * b2s.h -- C ABI of the B200-native dense-tableau two-phase simplex hot path.
+ *
+ * This is the drop-in boundary for the solve path of rik1599/SimplexOnCuda.  The reference has
+ * no C ABI of its own (its API is C++-linkage: include/problem.h, include/solver.h,
+ * include/twoPhaseMethod.h, include/reduction.cuh, include/gaussian.cuh, include/tabular.cuh);
+ * every entry point below names the reference interface (file:line under the reference tree)
+ * it replaces.  The C++ headers with the reference's own names (include/compat/) are thin shims
+ * over these functions.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; host pointers unless the name says `_device`;
+ *   - every function returns a b2s error code (B2S_OK == 0); nothing calls exit() (the
+ *     reference prints and exits on any CUDA error, src/error.cu:5-18);
+ *   - solver statuses are the reference's (include/twoPhaseMethod.h:5-8) plus two new ones;
+ *   - the tableau is "variable-major" exactly like the reference (include/tabular.cuh:5-30):
+ *     device row r holds tableau column r (row 0 = RHS b, rows 1..n structural variables, then
+ *     m slack rows, then m artificial rows), m contiguous values per row; reduced costs live in
+ *     a separate vector whose element 0 is the objective value.
+ */
+#ifndef B2S_H
+#define B2S_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- error codes (return values) ---------------------------------------------------------- */
+#define B2S_OK 0
+#define B2S_ERR_ARG 1    /* bad argument                                  */
+#define B2S_ERR_STATE 2  /* call out of order (e.g. iterate before build) */
+#define B2S_ERR_CUDA 3   /* CUDA runtime error, see b2s_last_error()      */
+#define B2S_ERR_NOMEM 4  /* device or host allocation failed              */
+#define B2S_ERR_NCCL 5   /* NCCL error (sharded solves)                   */
+#define B2S_ERR_NOGPU 6  /* no CUDA device: there is no CPU fallback      */
+
+/* ---- solver statuses (include/twoPhaseMethod.h:5-8, src/solver.cu:77) -------------------- */
+#define B2S_FEASIBLE 0
+#define B2S_INFEASIBLE (-1)
+#define B2S_UNBOUNDED (-2)
+#define B2S_DEGENERATE (-3)
+#define B2S_ITER_LIMIT (-4) /* new: pivot budget exhausted (the reference has no cap) */
+#define B2S_RUNNING (-10)   /* NOT_ENDED in src/solver.cu:77 */
+
+/* ---- options ----------------------------------------------------------------------------------- */
+#define B2S_F64 0
+#define B2S_F32 1
+
+#define B2S_RULE_REFERENCE 0 /* epsilon-tournament argmin, reference tie order (src/reduction.cu:10-104) */
+#define B2S_RULE_LOWEST 1    /* exact Dantzig minimum, lowest index among ties                           */
+#define B2S_RULE_BLAND 2     /* Bland's anti-cycling rule                                                */
+
+#define B2S_RAND_GLIBC 0 /* srand/rand of glibc: what the reference yields when built on Linux */
+#define B2S_RAND_MSVC 1  /* MSVC rand(): what the reference's published runs used (Windows)    */
+
+typedef struct b2s_options {
+    int device;           /* CUDA device ordinal (reference: always 0, main.cu:126)                 */
+    int dtype;            /* B2S_F64 (reference TYPE, include/macro.h:6) or B2S_F32                  */
+    int pivot_rule;       /* B2S_RULE_*                                                               */
+    int fold_artificials; /* 1: do not store the artificial rows (they are bitwise copies of the
+                             slack rows during phase 1); 0: reference layout with 1+n+2m rows        */
+    int skip_zero_rows;   /* 1: rows whose pivot-constraint entry is exactly 0 are not streamed      */
+    int use_graph;        /* 1: replay each batch of pivots as a CUDA graph                          */
+    int batch;            /* pivots enqueued between two host status polls; 0 = choose from size     */
+    long long max_pivots; /* total pivot cap for b2s_solve_two_phase; <= 0 = none (as the reference) */
+    long long trace_capacity; /* (q,p) pairs kept on the device for b2s_copy_trace; 0 = default 1<<20 */
+    int update_variant;   /* rank-1 update kernel variant (0 = default); for tuning/benchmarks       */
+    int reserved[7];
+} b2s_options;
+
+typedef struct b2s_stats {
+    long long pivots_phase1;
+    long long pivots_phase2;
+    unsigned long long trace_hash; /* FNV-1a over the (q,p) int32 pairs of every pivot            */
+    double seconds_total;          /* host wall time of the call                                   */
+    double seconds_load;           /* host->device transfer + tableau build                        */
+    double seconds_phase1;         /* device time, price-out + pivots of phase 1                   */
+    double seconds_phase2;
+    long long rows_streamed;       /* sum over pivots of tableau rows actually read+written        */
+    long long rows_total;          /* sum over pivots of stored tableau rows                       */
+    long long reserved[4];
+} b2s_stats;
+
+typedef struct b2s_solver b2s_solver; /* opaque */
+
+void b2s_default_options(b2s_options *opt);
+int b2s_create(const b2s_options *opt, b2s_solver **out);
+void b2s_destroy(b2s_solver *s);
+const char *b2s_last_error(const b2s_solver *s); /* s may be NULL: last error of the calling thread */
+int b2s_device_count(void);
+
+/* ---- problem input ------------------------------------------------------------------------- */
+/* Replaces the host->device path of fillTableu (src/twoPhaseMethod.cu:145-200) for a problem_t
+ * (include/problem.h:10-26): A is variable-major, A[j*m+i] = coefficient of variable j in
+ * constraint i; b[m]; c[n].  The arrays are pageable host memory and are only read. */
+int b2s_load_problem_host(b2s_solver *s, int n, int m, const double *A, const double *b, const double *c);
+
+/* Replaces generateRandomProblem (src/problem.cu:49-126) + generator kernels (src/generator.cu:9-32):
+ * the LP is generated on the device straight into the tableau, bit-identical to what the reference
+ * generates for the same three kernel seeds (b, c, A in that order).  64-bit stream offsets, so
+ * n*m may exceed 2^31 (the reference overflows int there, src/generator.cu:15). */
+int b2s_generate_problem_device(b2s_solver *s, int n, int m, const unsigned seeds[3], double lo, double hi);
+/* srand(seed); rand() x3 of src/problem.cu:63-67 for either C library. */
+void b2s_seed_triplet(unsigned seed, int rand_flavour, unsigned out[3]);
+/* Copy the current problem (as loaded or generated) back to host arrays; any pointer may be NULL. */
+int b2s_copy_problem(b2s_solver *s, double *A, double *b, double *c);
+
+/* ---- whole solve: twoPhaseMethod (src/twoPhaseMethod.cu:385-435) --------------------------- */
+/* Returns a b2s error code; *status receives FEASIBLE/INFEASIBLE/UNBOUNDED/DEGENERATE (or
+ * ITER_LIMIT).  x[n], *objective and basis[m] (0-based variable ids, src/solver.cu:105) are
+ * written when *status == B2S_FEASIBLE, like the reference writes solution/optimalValue;
+ * basis and stats may be NULL. */
+int b2s_solve_two_phase(b2s_solver *s, int *status, double *x, double *objective, int *basis, b2s_stats *stats);
+
+/* ---- stepping API (parity tests, benchmarks) --------------------------------------------------- */
+int b2s_build_phase1(b2s_solver *s);  /* fillTableu, src/twoPhaseMethod.cu:145-200                  */
+int b2s_price_out(b2s_solver *s);     /* updateObjectiveFunction, src/gaussian.cu:132-162           */
+int b2s_select_entering(b2s_solver *s); /* minElement(costs+1,...), src/solver.cu:86 (first pivot)  */
+/* Up to max_pivots iterations of src/solver.cu:78-126 (max_pivots < 0: until the phase ends).
+ * *status: B2S_RUNNING when the budget ran out first, else FEASIBLE (phase optimal) / UNBOUNDED. */
+int b2s_iterate(b2s_solver *s, long long max_pivots, int *status, long long *pivots_done);
+int b2s_phase1_verdict(b2s_solver *s, int *status); /* src/twoPhaseMethod.cu:258-282             */
+int b2s_switch_phase2(b2s_solver *s);               /* src/twoPhaseMethod.cu:285-337 (incl. price-out + select) */
+int b2s_extract_solution(b2s_solver *s, double *x, double *objective); /* :370-383               */
+
+/* ---- introspection ------------------------------------------------------------------------ */
+/* rows_active = reference `tabular->rows` (1+n+2m in phase 1, 1+n+m in phase 2); rows_stored =
+ * rows resident in HBM (differs when artificials are folded); ld = row pitch in elements. */
+int b2s_get_dims(const b2s_solver *s, int *n, int *m, long long *rows_active, long long *rows_stored, long long *ld);
+/* Dense copy of the active tableau in the reference's unfolded layout: rows_active x m. */
+int b2s_copy_tableau(b2s_solver *s, double *out);
+int b2s_copy_costs(b2s_solver *s, double *out); /* rows_active values, [0] = objective */
+int b2s_copy_basis(b2s_solver *s, int *out);    /* m values */
+int b2s_copy_trace(b2s_solver *s, int *qp_pairs, long long capacity, long long *length, unsigned long long *hash);
+int b2s_get_stats(b2s_solver *s, b2s_stats *stats);
+
+/* ---- kernel-level hooks (micro-benchmarks, unit parity) ------------------------------------ */
+/* minElement(vec, N, &idx) of src/reduction.cu:82-104 on a host vector: returns value and index. */
+int b2s_tournament(b2s_solver *s, const double *vec, long long n, double *value, int *index);
+/* Time `launches` launches of the fused rank-1 update (+cost update + next-pivot partial argmin)
+ * on the current tableau with a synthetic but representative pivot (dense s and pivot-row
+ * vectors); the tableau contents are destroyed.  ms_each[launches] receives per-launch CUDA
+ * event times measured on the solver's stream; flush_l2 != 0 rewrites a >L2 buffer between
+ * launches.  *bytes_per_launch = 2 * rows_stored * m * sizeof(real). */
+int b2s_bench_update(b2s_solver *s, int launches, int flush_l2, float *ms_each, double *bytes_per_launch);
+
+/* ---- sharded solves (constraint slabs over the GPUs of one box) ------------------------------ */
+#define B2S_NCCL_ID_BYTES 128
+int b2s_dist_unique_id(char id[B2S_NCCL_ID_BYTES]); /* rank 0 creates, the host layer broadcasts */
+/* One process per GPU; call after b2s_create and before loading/generating the problem.  Rank r
+ * owns constraints [r*m/world, (r+1)*m/world) of every tableau row; m/world must be a multiple of 512. */
+int b2s_dist_init(b2s_solver *s, int rank, int world, const char id[B2S_NCCL_ID_BYTES]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2S_H */

@@ -1,0 +1,1097 @@
+// b2s_solver.cu -- host driver of the B200 two-phase simplex and the C ABI (include/b2s.h).
+//
+// The host never takes part in a pivot: it enqueues batches of {ratio, gather, update} launches
+// (optionally replayed as one CUDA graph) and polls the device-resident DevState between
+// batches.  The reference's host-driven loop is src/solver.cu:128-149 / src/twoPhaseMethod.cu:385-435.
+#include "../../include/b2s.h"
+#include "b2s_generator.cuh"
+#include "b2s_kernels.cuh"
+
+#include <algorithm>
+#include <chrono>
+#include <climits>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#ifdef B2S_WITH_NCCL
+#include <nccl.h>
+#endif
+
+namespace b2s {
+
+static thread_local std::string g_thread_error;
+
+struct SolverBase {
+    b2s_options opt{};
+    std::string err;
+    virtual ~SolverBase() {}
+    virtual int load_host(int n, int m, const double* A, const double* b, const double* c) = 0;
+    virtual int generate(int n, int m, const unsigned seeds[3], double lo, double hi) = 0;
+    virtual int copy_problem(double* A, double* b, double* c) = 0;
+    virtual int build_phase1() = 0;
+    virtual int price_out() = 0;
+    virtual int select_entering() = 0;
+    virtual int iterate(long long max_pivots, int* status, long long* done) = 0;
+    virtual int phase1_verdict(int* status) = 0;
+    virtual int switch_phase2() = 0;
+    virtual int extract(double* x, double* obj) = 0;
+    virtual int solve(int* status, double* x, double* obj, int* basis, b2s_stats* stats) = 0;
+    virtual int get_dims(int* n, int* m, long long* ra, long long* rs, long long* ld) const = 0;
+    virtual int copy_tableau(double* out) = 0;
+    virtual int copy_costs(double* out) = 0;
+    virtual int copy_basis(int* out) = 0;
+    virtual int copy_trace(int* qp, long long cap, long long* len, unsigned long long* hash) = 0;
+    virtual int get_stats(b2s_stats* st) = 0;
+    virtual int tournament(const double* vec, long long n, double* value, int* index) = 0;
+    virtual int bench_update(int launches, int flush, float* ms, double* bytes) = 0;
+    virtual int dist_init(int rank, int world, const char* id) = 0;
+
+    int fail(int code, const char* fmt, ...)
+    {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof(buf), fmt, ap);
+        va_end(ap);
+        err = buf;
+        g_thread_error = buf;
+        return code;
+    }
+};
+
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+            return fail(e_ == cudaErrorMemoryAllocation ? B2S_ERR_NOMEM : B2S_ERR_CUDA, "%s:%d %s: %s", \
+                        __FILE__, __LINE__, #call, cudaGetErrorString(e_));                              \
+    } while (0)
+
+#ifdef B2S_WITH_NCCL
+#define NK(call)                                                                                      \
+    do {                                                                                              \
+        ncclResult_t r_ = (call);                                                                     \
+        if (r_ != ncclSuccess)                                                                        \
+            return fail(B2S_ERR_NCCL, "%s:%d %s: %s", __FILE__, __LINE__, #call, ncclGetErrorString(r_)); \
+    } while (0)
+#endif
+
+static double now_s()
+{
+    using namespace std::chrono;
+    return duration<double>(steady_clock::now().time_since_epoch()).count();
+}
+
+enum Stage { kEmpty = 0, kLoaded, kBuilt, kPriced, kReady, kPhaseDone };
+
+template <typename real>
+struct SolverImpl final : SolverBase {
+    int dev = 0;
+    int num_sms = 148;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int n = 0, m = 0, m_loc = 0, col0 = 0;
+    long long ld = 0, Rs = 0, R1 = 0, Rc = 0;
+    size_t cap_T = 0, cap_rows = 0, cap_cols = 0, cap_n = 0;  // allocated capacities
+    int phase = 0;
+    Stage stage = kEmpty;
+    bool folded = true;
+
+    real *T = nullptr, *cost = nullptr, *col = nullptr, *s = nullptr, *rowp = nullptr, *coef = nullptr, *c_dev = nullptr;
+    real *rslot_v = nullptr, *rslot_max = nullptr, *cslot_v = nullptr;
+    int *rslot_i = nullptr, *rslot_k = nullptr, *cslot_i = nullptr, *cslot_k = nullptr;
+    int *base = nullptr, *neg = nullptr, *verdict = nullptr;
+    double* x_dev = nullptr;
+    double* stage_dev = nullptr;  // fp64 staging for fp32 loads / exports
+    size_t cap_stage = 0;
+    DevState* st = nullptr;
+    DevState* st_host = nullptr;  // pinned
+    int2* trace = nullptr;
+    long long trace_cap = 0;
+    uint32_t* jump_tables = nullptr;
+    void* flush_buf = nullptr;
+    size_t flush_bytes = 0;
+
+    PivotParams<real> P{};
+    int upd_grid = 0;
+    cudaGraphExec_t graph_exec = nullptr;
+    int graph_batch = 0;
+    long long pivots_p1 = 0, pivots_p2 = 0;
+    double sec_load = 0, sec_p1 = 0, sec_p2 = 0;
+
+    // sharding
+    int rank = 0, world = 1;
+#ifdef B2S_WITH_NCCL
+    ncclComm_t comm = nullptr;
+#endif
+
+    ~SolverImpl() override { release(); }
+
+    void release()
+    {
+        cudaSetDevice(dev);
+        if (graph_exec) cudaGraphExecDestroy(graph_exec);
+        graph_exec = nullptr;
+        free_problem();
+        cudaFree(st);
+        cudaFreeHost(st_host);
+        cudaFree(trace);
+        cudaFree(jump_tables);
+        cudaFree(flush_buf);
+        cudaFree(verdict);
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        if (stream) cudaStreamDestroy(stream);
+#ifdef B2S_WITH_NCCL
+        if (comm) ncclCommDestroy(comm);
+        comm = nullptr;
+#endif
+        st = nullptr;
+        st_host = nullptr;
+        trace = nullptr;
+        jump_tables = nullptr;
+        flush_buf = nullptr;
+        verdict = nullptr;
+        ev0 = ev1 = nullptr;
+        stream = nullptr;
+    }
+
+    void free_problem()
+    {
+        cudaFree(T);
+        cudaFree(cost);
+        cudaFree(col);
+        cudaFree(s);
+        cudaFree(rowp);
+        cudaFree(coef);
+        cudaFree(c_dev);
+        cudaFree(rslot_v);
+        cudaFree(rslot_max);
+        cudaFree(cslot_v);
+        cudaFree(rslot_i);
+        cudaFree(rslot_k);
+        cudaFree(cslot_i);
+        cudaFree(cslot_k);
+        cudaFree(base);
+        cudaFree(neg);
+        cudaFree(x_dev);
+        cudaFree(stage_dev);
+        T = cost = col = s = rowp = coef = c_dev = rslot_v = rslot_max = cslot_v = nullptr;
+        rslot_i = rslot_k = cslot_i = cslot_k = base = neg = nullptr;
+        x_dev = stage_dev = nullptr;
+        cap_T = cap_rows = cap_cols = cap_n = cap_stage = 0;
+        stage = kEmpty;
+    }
+
+    int init()
+    {
+        int count = 0;
+        if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+            return fail(B2S_ERR_NOGPU, "no CUDA device visible: this library has no CPU fallback");
+        dev = opt.device;
+        if (dev < 0 || dev >= count) return fail(B2S_ERR_ARG, "device %d out of range (%d visible)", dev, count);
+        CK(cudaSetDevice(dev));
+        CK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+        CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        CK(cudaEventCreate(&ev0));
+        CK(cudaEventCreate(&ev1));
+        CK(cudaMalloc(&st, sizeof(DevState)));
+        CK(cudaMemset(st, 0, sizeof(DevState)));
+        CK(cudaHostAlloc(&st_host, sizeof(DevState), cudaHostAllocDefault));
+        CK(cudaMalloc(&verdict, 2 * sizeof(int)));
+        trace_cap = opt.trace_capacity > 0 ? opt.trace_capacity : (1ll << 20);
+        CK(cudaMalloc(&trace, sizeof(int2) * (size_t)trace_cap));
+        folded = opt.fold_artificials != 0;
+        return B2S_OK;
+    }
+
+    template <typename X>
+    int dmalloc(X** p, size_t count)
+    {
+        CK(cudaMalloc(p, sizeof(X) * std::max<size_t>(count, 1)));
+        return B2S_OK;
+    }
+
+    // (Re)allocate for an n x m problem and reset the solver state.
+    int prepare(int n_, int m_)
+    {
+        if (n_ < 1 || m_ < 1) return fail(B2S_ERR_ARG, "need n >= 1 and m >= 1 (got %d, %d)", n_, m_);
+        CK(cudaSetDevice(dev));
+        if (world > 1 && (m_ % (world * kSelBlock)) != 0)
+            return fail(B2S_ERR_ARG, "sharded solve needs constraints %% (world*512) == 0 (m=%d, world=%d)", m_, world);
+        n = n_;
+        m = m_;
+        m_loc = m / world;
+        col0 = rank * m_loc;
+        ld = ((long long)m_loc + 63) / 64 * 64;
+        R1 = 1 + (long long)n + 2ll * m;
+        Rs = folded ? 1 + (long long)n + m : R1;
+        Rc = R1;
+        phase = 0;
+        const size_t needT = (size_t)Rs * (size_t)ld;
+        if (needT > cap_T || (size_t)R1 > cap_rows || (size_t)ld > cap_cols || (size_t)n > cap_n) {
+            free_problem();
+            int rc;
+            if ((rc = dmalloc(&T, needT))) return rc;
+            if ((rc = dmalloc(&cost, (size_t)R1))) return rc;
+            if ((rc = dmalloc(&rowp, (size_t)R1))) return rc;
+            if ((rc = dmalloc(&col, (size_t)ld))) return rc;
+            if ((rc = dmalloc(&s, (size_t)ld))) return rc;
+            if ((rc = dmalloc(&coef, (size_t)ld))) return rc;
+            if ((rc = dmalloc(&neg, (size_t)ld))) return rc;
+            if ((rc = dmalloc(&c_dev, (size_t)n))) return rc;
+            if ((rc = dmalloc(&x_dev, (size_t)n))) return rc;
+            if ((rc = dmalloc(&base, (size_t)m))) return rc;
+            if ((rc = dmalloc(&rslot_v, kMaxSlots))) return rc;
+            if ((rc = dmalloc(&rslot_max, kMaxSlots))) return rc;
+            if ((rc = dmalloc(&rslot_i, kMaxSlots))) return rc;
+            if ((rc = dmalloc(&rslot_k, kMaxSlots))) return rc;
+            if ((rc = dmalloc(&cslot_v, kMaxSlots))) return rc;
+            if ((rc = dmalloc(&cslot_i, kMaxSlots))) return rc;
+            if ((rc = dmalloc(&cslot_k, kMaxSlots))) return rc;
+            cap_T = needT;
+            cap_rows = (size_t)R1;
+            cap_cols = (size_t)ld;
+            cap_n = (size_t)n;
+        }
+        CK(cudaMemsetAsync(st, 0, sizeof(DevState), stream));
+        pivots_p1 = pivots_p2 = 0;
+        sec_load = sec_p1 = sec_p2 = 0;
+        invalidate_graph();
+        fill_params();
+        return B2S_OK;
+    }
+
+    void invalidate_graph()
+    {
+        if (graph_exec) cudaGraphExecDestroy(graph_exec);
+        graph_exec = nullptr;
+        graph_batch = 0;
+    }
+
+    static int ceil_log2(long long v)
+    {
+        int l = 0;
+        while ((1ll << l) < v) ++l;
+        return l;
+    }
+
+    // ---- update-kernel variants --------------------------------------------------------------
+    struct Variant {
+        int vb, u, hint;
+    };
+    Variant variant() const
+    {
+        static const Variant table[] = {{16, 8, 0}, {16, 8, 1}, {32, 4, 0}, {32, 4, 1},
+                                        {32, 8, 0}, {16, 4, 0}, {16, 8, 2}, {32, 8, 1}};
+        int v = opt.update_variant;
+        if (v < 0 || v >= (int)(sizeof(table) / sizeof(table[0]))) v = 0;
+        return table[v];
+    }
+    typedef void (*UpdateFn)(PivotParams<real>);
+    template <int VB, int U, int HINT>
+    UpdateFn pick_skip() const
+    {
+        return opt.skip_zero_rows ? (UpdateFn)update_kernel<real, VB, U, HINT, true>
+                                  : (UpdateFn)update_kernel<real, VB, U, HINT, false>;
+    }
+    UpdateFn update_fn() const
+    {
+        switch (std::min(std::max(opt.update_variant, 0), 7)) {
+            default:
+            case 0: return pick_skip<16, 8, 0>();
+            case 1: return pick_skip<16, 8, 1>();
+            case 2: return pick_skip<32, 4, 0>();
+            case 3: return pick_skip<32, 4, 1>();
+            case 4: return pick_skip<32, 8, 0>();
+            case 5: return pick_skip<16, 4, 0>();
+            case 6: return pick_skip<16, 8, 2>();
+            case 7: return pick_skip<32, 8, 1>();
+        }
+    }
+
+    void fill_params()
+    {
+        P.T = T;
+        P.ld = ld;
+        P.n = n;
+        P.m = m;
+        P.m_loc = m_loc;
+        P.col0 = col0;
+        P.Rs = Rs;
+        P.Rc = Rc;
+        P.fold_from = folded ? 1 + (long long)n + m : LLONG_MAX;
+        P.cost = cost;
+        P.base = base;
+        P.col = col;
+        P.s = s;
+        P.rowp = rowp;
+        P.rslot_v = rslot_v;
+        P.rslot_i = rslot_i;
+        P.rslot_k = rslot_k;
+        P.rslot_max = rslot_max;
+        P.cslot_v = cslot_v;
+        P.cslot_i = cslot_i;
+        P.cslot_k = cslot_k;
+        P.st = st;
+        P.trace = trace;
+        P.trace_cap = trace_cap;
+        P.rule = opt.pivot_rule;
+        P.skip_zero = opt.skip_zero_rows;
+        P.Gm = (int)std::min<long long>(((long long)m + kSelBlock - 1) / kSelBlock, kMaxSlots);
+        P.Gm_loc0 = col0 / kSelBlock;
+        P.Gm_loc = world > 1 ? m_loc / kSelBlock : P.Gm;
+        P.Gc = (int)std::max<long long>(1, std::min<long long>((Rc - 1 + kSelBlock - 1) / kSelBlock, kMaxSlots));
+        // update-kernel tiling
+        const Variant v = variant();
+        const int ept = v.vb / (int)sizeof(real);
+        const long long thr_row = (ld + ept - 1) / ept;  // threads needed per row
+        const int l2 = std::min(9, ceil_log2(thr_row));
+        P.log2_tpr = l2;
+        const long long chunk_cols = (long long)ept << l2;
+        P.nchunks = (int)((ld + chunk_cols - 1) / chunk_cols);
+        const int rpp = kSelBlock >> l2;
+        int occ = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, update_fn(), kSelBlock, 0);
+        occ = std::max(1, occ);
+        int grid = num_sms * occ;
+        if (P.nchunks <= grid) grid = grid / P.nchunks * P.nchunks;
+        int tg = 4;
+        for (; tg > 1; tg >>= 1) {
+            const long long rows_tile = (long long)rpp * v.u * tg;
+            const long long nt = ((Rs + rows_tile - 1) / rows_tile) * P.nchunks;
+            if (nt >= 4ll * grid) break;
+        }
+        P.tile_groups = tg;
+        const long long rows_tile = (long long)rpp * v.u * tg;
+        P.ntiles = ((Rs + rows_tile - 1) / rows_tile) * P.nchunks;
+        upd_grid = (int)std::max<long long>(std::min<long long>(grid, P.ntiles), std::min(P.Gc, grid));
+        upd_grid = std::max(upd_grid, 1);
+    }
+
+    // ---- problem input -------------------------------------------------------------------------
+    int zero_fill_for_load()
+    {
+        // slack (and artificial) rows entirely; padding columns of the data rows.
+        const long long data_rows = 1 + (long long)n;
+        CK(cudaMemsetAsync(T + data_rows * ld, 0, sizeof(real) * (size_t)(Rs - data_rows) * (size_t)ld, stream));
+        if (ld > m_loc)
+            CK(cudaMemset2DAsync(T + m_loc, sizeof(real) * ld, 0, sizeof(real) * (ld - m_loc), (size_t)data_rows, stream));
+        return B2S_OK;
+    }
+
+    int ensure_stage(size_t count)
+    {
+        if (count > cap_stage) {
+            cudaFree(stage_dev);
+            stage_dev = nullptr;
+            cap_stage = 0;
+            CK(cudaMalloc(&stage_dev, sizeof(double) * count));
+            cap_stage = count;
+        }
+        return B2S_OK;
+    }
+
+    int load_host(int n_, int m_, const double* A, const double* b, const double* c) override
+    {
+        if (!A || !b || !c) return fail(B2S_ERR_ARG, "null problem array");
+        const double t0 = now_s();
+        int rc = prepare(n_, m_);
+        if (rc) return rc;
+        if ((rc = zero_fill_for_load())) return rc;
+        if (sizeof(real) == sizeof(double)) {
+            // rows 1..n <- A (variable-major, row pitch m), local slab columns only; row 0 <- b
+            CK(cudaMemcpy2DAsync(T + ld, sizeof(real) * ld, A + col0, sizeof(double) * m, sizeof(double) * m_loc,
+                                 (size_t)n, cudaMemcpyHostToDevice, stream));
+            CK(cudaMemcpyAsync(T, b + col0, sizeof(double) * m_loc, cudaMemcpyHostToDevice, stream));
+            CK(cudaMemcpyAsync(c_dev, c, sizeof(double) * n, cudaMemcpyHostToDevice, stream));
+        } else {
+            if ((rc = ensure_stage((size_t)(n + 1) * (size_t)m_loc + (size_t)n))) return rc;
+            CK(cudaMemcpy2DAsync(stage_dev + m_loc, sizeof(double) * m_loc, A + col0, sizeof(double) * m,
+                                 sizeof(double) * m_loc, (size_t)n, cudaMemcpyHostToDevice, stream));
+            CK(cudaMemcpyAsync(stage_dev, b + col0, sizeof(double) * m_loc, cudaMemcpyHostToDevice, stream));
+            double* cst = stage_dev + (size_t)(n + 1) * m_loc;
+            CK(cudaMemcpyAsync(cst, c, sizeof(double) * n, cudaMemcpyHostToDevice, stream));
+            convert_rows<<<1024, 256, 0, stream>>>(T, ld, stage_dev, (long long)m_loc, (long long)(n + 1), m_loc);
+            convert_rows<<<64, 256, 0, stream>>>(c_dev, (long long)n, cst, (long long)n, 1ll, n);
+        }
+        CK(cudaStreamSynchronize(stream));
+        stage = kLoaded;
+        sec_load = now_s() - t0;
+        return B2S_OK;
+    }
+
+    int ensure_jump_tables()
+    {
+        if (jump_tables) return B2S_OK;
+        std::vector<uint32_t> host;
+        xorwow_build_jump_tables(host);
+        CK(cudaMalloc(&jump_tables, host.size() * sizeof(uint32_t)));
+        CK(cudaMemcpy(jump_tables, host.data(), host.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        return B2S_OK;
+    }
+
+    int generate(int n_, int m_, const unsigned seeds[3], double lo, double hi) override
+    {
+        const double t0 = now_s();
+        int rc = prepare(n_, m_);
+        if (rc) return rc;
+        if ((rc = ensure_jump_tables())) return rc;
+        if ((rc = zero_fill_for_load())) return rc;
+        const double span = hi - lo;
+        {  // b -> row 0 (local slab): element id = global constraint index
+            const long long nthreads = ((long long)m_loc + kVecRun - 1) / kVecRun;
+            generate_vector_kernel<real><<<(unsigned)((nthreads + 255) / 256), 256, 0, stream>>>(
+                T, (long long)m_loc, (long long)col0, seeds[0], lo, span, jump_tables);
+        }
+        {  // c (replicated on every rank)
+            const long long nthreads = ((long long)n + kVecRun - 1) / kVecRun;
+            generate_vector_kernel<real><<<(unsigned)((nthreads + 255) / 256), 256, 0, stream>>>(
+                c_dev, (long long)n, 0ll, seeds[1], lo, span, jump_tables);
+        }
+        {
+            dim3 grid((unsigned)((m_loc + 255) / 256), (unsigned)((n + kMatRun - 1) / kMatRun));
+            generate_matrix_kernel<real><<<grid, 256, 0, stream>>>(T, ld, 1ll, n, m_loc, col0, seeds[2], lo, span, jump_tables);
+        }
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(stream));
+        stage = kLoaded;
+        sec_load = now_s() - t0;
+        return B2S_OK;
+    }
+
+    int copy_problem(double* A, double* b, double* c) override
+    {
+        if (stage != kLoaded) return fail(B2S_ERR_STATE, "copy_problem is only valid between load/generate and build");
+        if (world > 1) return fail(B2S_ERR_STATE, "copy_problem is not available on a sharded solver");
+        CK(cudaSetDevice(dev));
+        if (sizeof(real) == sizeof(double)) {
+            if (A)
+                CK(cudaMemcpy2D(A, sizeof(double) * m, T + ld, sizeof(real) * ld, sizeof(double) * m, (size_t)n,
+                                cudaMemcpyDeviceToHost));
+            if (b) CK(cudaMemcpy(b, T, sizeof(double) * m, cudaMemcpyDeviceToHost));
+            if (c) CK(cudaMemcpy(c, c_dev, sizeof(double) * n, cudaMemcpyDeviceToHost));
+        } else {
+            int rc = ensure_stage((size_t)(n + 1) * (size_t)m + (size_t)n);
+            if (rc) return rc;
+            widen_rows<<<1024, 256, 0, stream>>>(stage_dev, (long long)m, T, ld, (long long)(n + 1), m);
+            widen_rows<<<64, 256, 0, stream>>>(stage_dev + (size_t)(n + 1) * m, (long long)n, c_dev, (long long)n, 1ll, n);
+            CK(cudaStreamSynchronize(stream));
+            if (b) CK(cudaMemcpy(b, stage_dev, sizeof(double) * m, cudaMemcpyDeviceToHost));
+            if (A) CK(cudaMemcpy(A, stage_dev + m, sizeof(double) * (size_t)n * m, cudaMemcpyDeviceToHost));
+            if (c) CK(cudaMemcpy(c, stage_dev + (size_t)(n + 1) * m, sizeof(double) * n, cudaMemcpyDeviceToHost));
+        }
+        return B2S_OK;
+    }
+
+    // ---- phases ------------------------------------------------------------------------------
+    int build_phase1() override
+    {
+        if (stage != kLoaded) return fail(B2S_ERR_STATE, "build_phase1 needs a freshly loaded or generated problem");
+        CK(cudaSetDevice(dev));
+        Rc = R1;
+        phase = 1;
+        fill_params();
+        invalidate_graph();
+        CK(cudaMemsetAsync(st, 0, sizeof(DevState), stream));
+        const long long work = std::max<long long>(std::max<long long>(m, Rc), m_loc);
+        build_misc_kernel<real><<<(unsigned)((work + 255) / 256), 256, 0, stream>>>(P, neg, folded ? 0 : 1);
+        negate_kernel<real><<<num_sms * 4, 256, 0, stream>>>(P, neg);
+        state_reset_kernel<<<1, 1, 0, stream>>>(st, 1);
+        CK(cudaGetLastError());
+        stage = kBuilt;
+        return B2S_OK;
+    }
+
+    int price_out() override
+    {
+        if (stage != kBuilt) return fail(B2S_ERR_STATE, "price_out follows build_phase1 / switch_phase2");
+        CK(cudaSetDevice(dev));
+        coef_kernel<real><<<(unsigned)((m_loc + 255) / 256), 256, 0, stream>>>(P, coef);
+        const long long threads = Rc * 32;
+        const unsigned blocks = (unsigned)((threads + 255) / 256);
+#ifdef B2S_WITH_NCCL
+        if (world > 1) {
+            // Chain the running sums through the ranks in ascending constraint order so the result is
+            // bit-identical to the single-GPU order (slabs are multiples of 64 constraints).
+            for (int r = 0; r < world; ++r) {
+                if (r == rank) priceout_kernel<real><<<blocks, 256, 0, stream>>>(P, coef);
+                NK(ncclBroadcast(cost, cost, (size_t)Rc * sizeof(real), ncclChar, r, comm, stream));
+            }
+        } else
+#endif
+        {
+            priceout_kernel<real><<<blocks, 256, 0, stream>>>(P, coef);
+        }
+        CK(cudaGetLastError());
+        stage = kPriced;
+        return B2S_OK;
+    }
+
+    int select_entering() override
+    {
+        if (stage != kPriced) return fail(B2S_ERR_STATE, "select_entering follows price_out");
+        CK(cudaSetDevice(dev));
+        select_kernel<real><<<P.Gc, kSelBlock, 0, stream>>>(P);
+        CK(cudaGetLastError());
+        stage = kReady;
+        return B2S_OK;
+    }
+
+    int enqueue_pivot()
+    {
+#ifdef B2S_WITH_NCCL
+        if (world > 1) return enqueue_pivot_sharded();
+#endif
+        ratio_kernel<real, false><<<P.Gm, kSelBlock, 0, stream>>>(P);
+        const long long work = std::max(Rs, ld);
+        gather_kernel<real, false><<<(unsigned)((work + 255) / 256), 256, 0, stream>>>(P);
+        update_fn()<<<upd_grid, kSelBlock, 0, stream>>>(P);
+        return B2S_OK;
+    }
+
+#ifdef B2S_WITH_NCCL
+    // One pivot on a constraint-sharded tableau.  Two small exchanges per pivot:
+    //  (1) all-gather of the ratio-test stage-1 block winners (the epsilon tournament is not
+    //      associative, so every rank replays the reference's stage 2 on the full slot list);
+    //  (2) the owner of constraint p publishes the raw pivot-constraint vector through an integer
+    //      sum all-reduce in which the other ranks contribute zeros (bit-exact broadcast whose root
+    //      is only known on the device).
+    int enqueue_pivot_sharded()
+    {
+        ratio_kernel<real, true><<<P.Gm_loc, kSelBlock, 0, stream>>>(P);
+        const size_t cnt = (size_t)P.Gm_loc;
+        const size_t off = (size_t)P.Gm_loc0;
+        NK(ncclGroupStart());
+        NK(ncclAllGather(rslot_v + off, rslot_v, cnt * sizeof(real), ncclChar, comm, stream));
+        NK(ncclAllGather(rslot_max + off, rslot_max, cnt * sizeof(real), ncclChar, comm, stream));
+        NK(ncclAllGather(rslot_i + off, rslot_i, cnt * sizeof(int), ncclChar, comm, stream));
+        NK(ncclAllGather(rslot_k + off, rslot_k, cnt * sizeof(int), ncclChar, comm, stream));
+        NK(ncclGroupEnd());
+        ratio_finish_kernel<real><<<1, kSelBlock, 0, stream>>>(P);
+        gather_kernel<real, true><<<(unsigned)((Rs + 255) / 256), 256, 0, stream>>>(P);
+        NK(ncclAllReduce(rowp, rowp, (size_t)Rs, sizeof(real) == 8 ? ncclUint64 : ncclUint32, ncclSum, comm, stream));
+        svec_kernel<real><<<(unsigned)((ld + 255) / 256), 256, 0, stream>>>(P);
+        update_fn()<<<upd_grid, kSelBlock, 0, stream>>>(P);
+        return B2S_OK;
+    }
+#endif
+
+    int pick_batch() const
+    {
+        if (opt.batch > 0) return opt.batch;
+        const double bytes = 2.0 * (double)Rs * (double)ld * sizeof(real);
+        const double t = std::max(12e-6, bytes / 5.0e12);
+        return (int)std::min(256.0, std::max(4.0, 3e-3 / t));
+    }
+
+    int launch_batch(int batch)
+    {
+        const bool graphable = opt.use_graph && world == 1;
+        if (!graphable) {
+            for (int k = 0; k < batch; ++k) {
+                int rc = enqueue_pivot();
+                if (rc) return rc;
+            }
+            CK(cudaGetLastError());
+            return B2S_OK;
+        }
+        if (!graph_exec || graph_batch != batch) {
+            invalidate_graph();
+            cudaGraph_t graph = nullptr;
+            CK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+            for (int k = 0; k < batch; ++k) enqueue_pivot();
+            CK(cudaStreamEndCapture(stream, &graph));
+            cudaError_t e = cudaGraphInstantiate(&graph_exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (e != cudaSuccess) return fail(B2S_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
+            graph_batch = batch;
+        }
+        CK(cudaGraphLaunch(graph_exec, stream));
+        return B2S_OK;
+    }
+
+    int fetch_state()
+    {
+        CK(cudaMemcpyAsync(st_host, st, sizeof(DevState), cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        return B2S_OK;
+    }
+
+    int iterate(long long max_pivots, int* status, long long* done) override
+    {
+        if (stage != kReady && stage != kPhaseDone) return fail(B2S_ERR_STATE, "iterate follows select_entering");
+        CK(cudaSetDevice(dev));
+        int rc = fetch_state();
+        if (rc) return rc;
+        const long long start = st_host->pivots;
+        if (done) *done = 0;
+        if (st_host->status != kRunning || max_pivots == 0) {
+            if (status) *status = st_host->status;
+            return B2S_OK;
+        }
+        const long long limit = max_pivots < 0 ? LLONG_MAX : start + max_pivots;
+        CK(cudaMemcpyAsync(&st->limit, &limit, sizeof(long long), cudaMemcpyHostToDevice, stream));
+        CK(cudaEventRecord(ev0, stream));
+        const int full = pick_batch();
+        while (true) {
+            const long long left = limit - st_host->pivots;
+            int batch = full;
+            if (!(opt.use_graph && world == 1) && left < batch) batch = (int)left;
+            if ((rc = launch_batch(batch))) return rc;
+            if ((rc = fetch_state())) return rc;
+            if (st_host->status != kRunning || st_host->pivots >= limit) break;
+        }
+        CK(cudaEventRecord(ev1, stream));
+        CK(cudaEventSynchronize(ev1));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, ev0, ev1));
+        const long long made = st_host->pivots - start;
+        if (phase == 2) {
+            pivots_p2 += made;
+            sec_p2 += ms * 1e-3;
+        } else {
+            pivots_p1 += made;
+            sec_p1 += ms * 1e-3;
+        }
+        if (done) *done = made;
+        if (status) *status = st_host->status;
+        if (st_host->status != kRunning) stage = kPhaseDone;
+        return B2S_OK;
+    }
+
+    int phase1_verdict(int* status) override
+    {
+        if (phase != 1 || (stage != kReady && stage != kPhaseDone))
+            return fail(B2S_ERR_STATE, "phase1_verdict follows the phase-1 pivots");
+        CK(cudaSetDevice(dev));
+        CK(cudaMemsetAsync(verdict, 0, 2 * sizeof(int), stream));
+        verdict_kernel<real><<<(unsigned)((m + 255) / 256), 256, 0, stream>>>(P, verdict);
+        int h[2] = {0, 0};
+        CK(cudaMemcpyAsync(h, verdict, sizeof(h), cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        *status = h[0] ? B2S_INFEASIBLE : (h[1] > 0 ? B2S_DEGENERATE : B2S_FEASIBLE);
+        return B2S_OK;
+    }
+
+    int switch_phase2() override
+    {
+        if (phase != 1 || (stage != kReady && stage != kPhaseDone))
+            return fail(B2S_ERR_STATE, "switch_phase2 follows phase 1");
+        CK(cudaSetDevice(dev));
+        phase = 2;
+        Rc = 1 + (long long)n + m;  // rows -= cols (src/twoPhaseMethod.cu:288)
+        Rs = Rc;                    // unfolded layout: the trailing artificial rows are simply ignored
+        fill_params();
+        invalidate_graph();
+        phase2_costs_kernel<real><<<(unsigned)(((long long)n + m + 255) / 256), 256, 0, stream>>>(P, c_dev);
+        state_reset_kernel<<<1, 1, 0, stream>>>(st, 0);  // back to RUNNING, keep counters / hash
+        CK(cudaGetLastError());
+        stage = kBuilt;
+        return B2S_OK;
+    }
+
+    int extract(double* x, double* obj) override
+    {
+        if (stage == kEmpty || stage == kLoaded) return fail(B2S_ERR_STATE, "nothing to extract");
+        CK(cudaSetDevice(dev));
+        CK(cudaMemsetAsync(x_dev, 0, sizeof(double) * n, stream));
+        solution_kernel<real><<<(unsigned)((m_loc + 255) / 256), 256, 0, stream>>>(P, x_dev);
+#ifdef B2S_WITH_NCCL
+        if (world > 1) NK(ncclAllReduce(x_dev, x_dev, (size_t)n, ncclDouble, ncclSum, comm, stream));
+#endif
+        real c0;
+        CK(cudaMemcpyAsync(&c0, cost, sizeof(real), cudaMemcpyDeviceToHost, stream));
+        if (x) CK(cudaMemcpyAsync(x, x_dev, sizeof(double) * n, cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        if (obj) *obj = (double)c0;
+        return B2S_OK;
+    }
+
+    int solve(int* status, double* x, double* obj, int* basis, b2s_stats* stats) override
+    {
+        const double t0 = now_s();
+        int rc, stt = B2S_RUNNING;
+        long long done = 0;
+        const long long cap = opt.max_pivots > 0 ? opt.max_pivots : -1;
+        if ((rc = build_phase1())) return rc;
+        if ((rc = price_out())) return rc;
+        if ((rc = select_entering())) return rc;
+        if ((rc = iterate(cap, &stt, &done))) return rc;
+        int result;
+        if (stt == B2S_RUNNING) {
+            result = B2S_ITER_LIMIT;
+        } else {
+            if ((rc = phase1_verdict(&result))) return rc;  // the phase-1 solve status is ignored (src/twoPhaseMethod.cu:258)
+            if (result == B2S_FEASIBLE) {
+                if ((rc = switch_phase2())) return rc;
+                if ((rc = price_out())) return rc;
+                if ((rc = select_entering())) return rc;
+                const long long left = cap < 0 ? -1 : std::max<long long>(0, cap - done);
+                if ((rc = iterate(left, &stt, &done))) return rc;
+                if (stt == B2S_RUNNING)
+                    result = B2S_ITER_LIMIT;
+                else if (stt != B2S_FEASIBLE)
+                    result = stt;
+                else if ((rc = extract(x, obj)))
+                    return rc;
+            }
+        }
+        if (basis && (rc = copy_basis(basis))) return rc;
+        if (status) *status = result;
+        if (stats) {
+            get_stats(stats);
+            stats->seconds_total = now_s() - t0 + sec_load;
+        }
+        return B2S_OK;
+    }
+
+    // ---- introspection -----------------------------------------------------------------------
+    int get_dims(int* n_, int* m_, long long* ra, long long* rs, long long* ld_) const override
+    {
+        if (n_) *n_ = n;
+        if (m_) *m_ = m;
+        if (ra) *ra = Rc;
+        if (rs) *rs = Rs;
+        if (ld_) *ld_ = ld;
+        return B2S_OK;
+    }
+
+    int copy_tableau(double* out) override
+    {
+        if (stage == kEmpty) return fail(B2S_ERR_STATE, "no problem loaded");
+        if (world > 1) return fail(B2S_ERR_STATE, "copy_tableau is not available on a sharded solver");
+        CK(cudaSetDevice(dev));
+        const size_t count = (size_t)Rc * (size_t)m;
+        int rc = ensure_stage(count);
+        if (rc) return rc;
+        export_kernel<real><<<num_sms * 8, 256, 0, stream>>>(P, stage_dev);
+        CK(cudaMemcpyAsync(out, stage_dev, sizeof(double) * count, cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        return B2S_OK;
+    }
+
+    int copy_costs(double* out) override
+    {
+        if (stage == kEmpty) return fail(B2S_ERR_STATE, "no problem loaded");
+        CK(cudaSetDevice(dev));
+        std::vector<real> tmp((size_t)Rc);
+        CK(cudaMemcpyAsync(tmp.data(), cost, sizeof(real) * (size_t)Rc, cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        for (long long i = 0; i < Rc; ++i) out[i] = (double)tmp[(size_t)i];
+        return B2S_OK;
+    }
+
+    int copy_basis(int* out) override
+    {
+        if (stage == kEmpty || stage == kLoaded) return fail(B2S_ERR_STATE, "no basis yet");
+        CK(cudaSetDevice(dev));
+        CK(cudaMemcpyAsync(out, base, sizeof(int) * (size_t)m, cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        return B2S_OK;
+    }
+
+    int copy_trace(int* qp, long long cap, long long* len, unsigned long long* hash) override
+    {
+        CK(cudaSetDevice(dev));
+        int rc = fetch_state();
+        if (rc) return rc;
+        const long long have = st_host->pivots;
+        if (len) *len = have;
+        if (hash) *hash = st_host->hash;
+        const long long cnt = std::min(std::min(have, cap), trace_cap);
+        if (qp && cnt > 0) {
+            CK(cudaMemcpyAsync(qp, trace, sizeof(int2) * (size_t)cnt, cudaMemcpyDeviceToHost, stream));
+            CK(cudaStreamSynchronize(stream));
+        }
+        return B2S_OK;
+    }
+
+    int get_stats(b2s_stats* out) override
+    {
+        CK(cudaSetDevice(dev));
+        int rc = fetch_state();
+        if (rc) return rc;
+        memset(out, 0, sizeof(*out));
+        out->pivots_phase1 = pivots_p1;
+        out->pivots_phase2 = pivots_p2;
+        out->trace_hash = st_host->hash;
+        out->seconds_load = sec_load;
+        out->seconds_phase1 = sec_p1;
+        out->seconds_phase2 = sec_p2;
+        out->rows_streamed = st_host->rows_streamed;
+        out->rows_total = pivots_p1 * (folded ? 1 + (long long)n + m : R1) + pivots_p2 * (1 + (long long)n + m);
+        return B2S_OK;
+    }
+
+    // ---- kernel-level hooks ------------------------------------------------------------------
+    int tournament(const double* vec, long long cnt, double* value, int* index) override
+    {
+        if (cnt < 1 || !vec) return fail(B2S_ERR_ARG, "tournament needs a non-empty vector");
+        CK(cudaSetDevice(dev));
+        std::vector<real> h((size_t)cnt + 1);
+        h[0] = 0;
+        for (long long i = 0; i < cnt; ++i) h[(size_t)i + 1] = (real)vec[i];
+        real* dcost = nullptr;
+        real* dv = nullptr;
+        int *di = nullptr, *dk = nullptr;
+        DevState* dst = nullptr;
+        CK(cudaMalloc(&dcost, sizeof(real) * ((size_t)cnt + 1)));
+        CK(cudaMalloc(&dv, sizeof(real) * kMaxSlots));
+        CK(cudaMalloc(&di, sizeof(int) * kMaxSlots));
+        CK(cudaMalloc(&dk, sizeof(int) * kMaxSlots));
+        CK(cudaMalloc(&dst, sizeof(DevState)));
+        CK(cudaMemset(dst, 0, sizeof(DevState)));
+        CK(cudaMemcpy(dcost, h.data(), sizeof(real) * ((size_t)cnt + 1), cudaMemcpyHostToDevice));
+        PivotParams<real> Q{};
+        Q.cost = dcost;
+        Q.Rc = cnt + 1;
+        Q.fold_from = LLONG_MAX;
+        Q.cslot_v = dv;
+        Q.cslot_i = di;
+        Q.cslot_k = dk;
+        Q.st = dst;
+        Q.rule = opt.pivot_rule;
+        Q.Gc = (int)std::max<long long>(1, std::min<long long>((cnt + kSelBlock - 1) / kSelBlock, kMaxSlots));
+        select_kernel<real><<<Q.Gc, kSelBlock, 0, stream>>>(Q);
+        DevState hs;
+        CK(cudaMemcpyAsync(&hs, dst, sizeof(DevState), cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        if (value) *value = hs.cq;
+        if (index) *index = hs.q;
+        cudaFree(dcost);
+        cudaFree(dv);
+        cudaFree(di);
+        cudaFree(dk);
+        cudaFree(dst);
+        return B2S_OK;
+    }
+
+    int bench_update(int launches, int flush, float* ms, double* bytes) override
+    {
+        if (stage == kEmpty) return fail(B2S_ERR_STATE, "bench_update needs a loaded problem (dimensions)");
+        CK(cudaSetDevice(dev));
+        if (flush && !flush_buf) {
+            flush_bytes = 512ull << 20;
+            CK(cudaMalloc(&flush_buf, flush_bytes));
+        }
+        const long long work = std::max(Rs, ld);
+        bench_fill_kernel<real><<<(unsigned)((work + 255) / 256), 256, 0, stream>>>(P);
+        std::vector<cudaEvent_t> ev(2 * (size_t)launches);
+        for (auto& e : ev) CK(cudaEventCreate(&e));
+        for (int k = 0; k < launches; ++k) {
+            if (flush) CK(cudaMemsetAsync(flush_buf, k & 0xff, flush_bytes, stream));
+            CK(cudaEventRecord(ev[2 * k], stream));
+            update_fn()<<<upd_grid, kSelBlock, 0, stream>>>(P);
+            CK(cudaEventRecord(ev[2 * k + 1], stream));
+        }
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(stream));
+        for (int k = 0; k < launches; ++k) CK(cudaEventElapsedTime(ms + k, ev[2 * k], ev[2 * k + 1]));
+        for (auto& e : ev) cudaEventDestroy(e);
+        if (bytes) *bytes = 2.0 * (double)Rs * (double)m_loc * sizeof(real);
+        stage = kEmpty;  // tableau contents destroyed
+        CK(cudaMemsetAsync(st, 0, sizeof(DevState), stream));
+        CK(cudaStreamSynchronize(stream));
+        return B2S_OK;
+    }
+
+    int dist_init(int rank_, int world_, const char* id) override
+    {
+#ifdef B2S_WITH_NCCL
+        if (world_ < 1 || rank_ < 0 || rank_ >= world_) return fail(B2S_ERR_ARG, "bad rank/world %d/%d", rank_, world_);
+        CK(cudaSetDevice(dev));
+        if (comm) {
+            ncclCommDestroy(comm);
+            comm = nullptr;
+        }
+        rank = rank_;
+        world = world_;
+        if (world > 1) {
+            ncclUniqueId uid;
+            static_assert(sizeof(uid) == B2S_NCCL_ID_BYTES, "unique id size");
+            memcpy(&uid, id, sizeof(uid));
+            NK(ncclCommInitRank(&comm, world, uid, rank));
+        }
+        free_problem();
+        return B2S_OK;
+#else
+        (void)rank_;
+        (void)world_;
+        (void)id;
+        return fail(B2S_ERR_NCCL, "library built without NCCL");
+#endif
+    }
+
+};
+
+}  // namespace b2s
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+using b2s::SolverBase;
+
+struct b2s_solver {
+    SolverBase* impl;
+};
+
+extern "C" {
+
+void b2s_default_options(b2s_options* opt)
+{
+    memset(opt, 0, sizeof(*opt));
+    opt->device = 0;
+    opt->dtype = B2S_F64;
+    opt->pivot_rule = B2S_RULE_REFERENCE;
+    opt->fold_artificials = 1;
+    opt->skip_zero_rows = 0;
+    opt->use_graph = 1;
+    opt->batch = 0;
+    opt->max_pivots = 0;
+    opt->trace_capacity = 0;
+    opt->update_variant = 0;
+}
+
+int b2s_device_count(void)
+{
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) return 0;
+    return count;
+}
+
+int b2s_create(const b2s_options* opt, b2s_solver** out)
+{
+    if (!out) return B2S_ERR_ARG;
+    *out = nullptr;
+    b2s_options o;
+    if (opt)
+        o = *opt;
+    else
+        b2s_default_options(&o);
+    if (o.pivot_rule < 0 || o.pivot_rule > 2) {
+        b2s::g_thread_error = "unknown pivot_rule";
+        return B2S_ERR_ARG;
+    }
+    SolverBase* impl = nullptr;
+    int rc;
+    if (o.dtype == B2S_F64) {
+        auto* p = new b2s::SolverImpl<double>();
+        p->opt = o;
+        rc = p->init();
+        impl = p;
+    } else if (o.dtype == B2S_F32) {
+        auto* p = new b2s::SolverImpl<float>();
+        p->opt = o;
+        rc = p->init();
+        impl = p;
+    } else {
+        b2s::g_thread_error = "unknown dtype";
+        return B2S_ERR_ARG;
+    }
+    if (rc != B2S_OK) {
+        delete impl;
+        return rc;
+    }
+    *out = new b2s_solver{impl};
+    return B2S_OK;
+}
+
+void b2s_destroy(b2s_solver* s)
+{
+    if (!s) return;
+    delete s->impl;
+    delete s;
+}
+
+const char* b2s_last_error(const b2s_solver* s)
+{
+    if (s && s->impl) return s->impl->err.c_str();
+    return b2s::g_thread_error.c_str();
+}
+
+#define B2S_FWD(expr)               \
+    if (!s || !s->impl) return B2S_ERR_ARG; \
+    return s->impl->expr
+
+int b2s_load_problem_host(b2s_solver* s, int n, int m, const double* A, const double* b, const double* c) { B2S_FWD(load_host(n, m, A, b, c)); }
+int b2s_generate_problem_device(b2s_solver* s, int n, int m, const unsigned seeds[3], double lo, double hi) { B2S_FWD(generate(n, m, seeds, lo, hi)); }
+int b2s_copy_problem(b2s_solver* s, double* A, double* b, double* c) { B2S_FWD(copy_problem(A, b, c)); }
+int b2s_solve_two_phase(b2s_solver* s, int* status, double* x, double* objective, int* basis, b2s_stats* stats) { B2S_FWD(solve(status, x, objective, basis, stats)); }
+int b2s_build_phase1(b2s_solver* s) { B2S_FWD(build_phase1()); }
+int b2s_price_out(b2s_solver* s) { B2S_FWD(price_out()); }
+int b2s_select_entering(b2s_solver* s) { B2S_FWD(select_entering()); }
+int b2s_iterate(b2s_solver* s, long long max_pivots, int* status, long long* pivots_done) { B2S_FWD(iterate(max_pivots, status, pivots_done)); }
+int b2s_phase1_verdict(b2s_solver* s, int* status)
+{
+    if (!status) return B2S_ERR_ARG;
+    B2S_FWD(phase1_verdict(status));
+}
+int b2s_switch_phase2(b2s_solver* s) { B2S_FWD(switch_phase2()); }
+int b2s_extract_solution(b2s_solver* s, double* x, double* objective) { B2S_FWD(extract(x, objective)); }
+int b2s_get_dims(const b2s_solver* s, int* n, int* m, long long* rows_active, long long* rows_stored, long long* ld) { B2S_FWD(get_dims(n, m, rows_active, rows_stored, ld)); }
+int b2s_copy_tableau(b2s_solver* s, double* out) { B2S_FWD(copy_tableau(out)); }
+int b2s_copy_costs(b2s_solver* s, double* out) { B2S_FWD(copy_costs(out)); }
+int b2s_copy_basis(b2s_solver* s, int* out) { B2S_FWD(copy_basis(out)); }
+int b2s_copy_trace(b2s_solver* s, int* qp_pairs, long long capacity, long long* length, unsigned long long* hash) { B2S_FWD(copy_trace(qp_pairs, capacity, length, hash)); }
+int b2s_get_stats(b2s_solver* s, b2s_stats* stats)
+{
+    if (!stats) return B2S_ERR_ARG;
+    B2S_FWD(get_stats(stats));
+}
+int b2s_tournament(b2s_solver* s, const double* vec, long long n, double* value, int* index) { B2S_FWD(tournament(vec, n, value, index)); }
+int b2s_bench_update(b2s_solver* s, int launches, int flush_l2, float* ms_each, double* bytes_per_launch)
+{
+    if (launches < 1 || !ms_each) return B2S_ERR_ARG;
+    B2S_FWD(bench_update(launches, flush_l2, ms_each, bytes_per_launch));
+}
+int b2s_dist_init(b2s_solver* s, int rank, int world, const char id[B2S_NCCL_ID_BYTES]) { B2S_FWD(dist_init(rank, world, id)); }
+
+int b2s_dist_unique_id(char id[B2S_NCCL_ID_BYTES])
+{
+#ifdef B2S_WITH_NCCL
+    ncclUniqueId uid;
+    if (ncclGetUniqueId(&uid) != ncclSuccess) return B2S_ERR_NCCL;
+    memcpy(id, &uid, sizeof(uid));
+    return B2S_OK;
+#else
+    (void)id;
+    return B2S_ERR_NCCL;
+#endif
+}
+
+/* srand(seed); rand() x3 (src/problem.cu:63-67) for glibc's TYPE_3 generator or MSVC's LCG. */
+void b2s_seed_triplet(unsigned seed, int rand_flavour, unsigned out[3])
+{
+    if (rand_flavour == B2S_RAND_MSVC) {
+        unsigned state = seed;
+        for (int k = 0; k < 3; ++k) {
+            state = state * 214013u + 2531011u;
+            out[k] = (state >> 16) & 0x7fffu;
+        }
+        return;
+    }
+    // glibc random_r, TYPE_3: 31-word additive feedback register seeded by a Lehmer sequence,
+    // 310 outputs discarded, result = word >> 1.
+    int reg[34];
+    reg[0] = seed ? (int)seed : 1;
+    for (int i = 1; i < 31; ++i) {
+        const long long hi = reg[i - 1] / 127773, lo = reg[i - 1] % 127773;
+        long long word = 16807 * lo - 2836 * hi;
+        if (word < 0) word += 2147483647;
+        reg[i] = (int)word;
+    }
+    unsigned ring[34];
+    for (int i = 0; i < 31; ++i) ring[i] = (unsigned)reg[i];
+    for (int i = 31; i < 34; ++i) ring[i] = ring[i - 31];
+    // sliding window of the last 34 words
+    std::vector<unsigned> w(ring, ring + 34);
+    for (int i = 34; i < 344 + 3; ++i) w.push_back(w[i - 31] + w[i - 3]);
+    for (int k = 0; k < 3; ++k) out[k] = w[344 + k] >> 1;
+}
+
+}  // extern "C"

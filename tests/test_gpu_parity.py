@@ -1,0 +1,226 @@
+"""GPU parity tests (run on the B200 box): the CUDA hot path, called through the C ABI, against the
+serial oracle on the same seeded inputs -- bit-exact pivot sequence, basis, status, tableau and
+cost vector; objective identical (fp64)."""
+import io
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle_py as O
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+PUB = json.load(open(os.path.join(HERE, "golden", "published_pivot_counts.json")))
+ORC = json.load(open(os.path.join(HERE, "golden", "oracle_results.json")))
+EXAMPLES = json.load(open(os.path.join(HERE, "golden", "examples.json")))
+
+
+@pytest.fixture(scope="module")
+def S():
+    import simplexoncuda_b200 as S
+    return S
+
+
+def same(a, b):
+    """Value-exact comparison (+0.0 == -0.0; NaN never expected)."""
+    return np.array_equal(np.asarray(a), np.asarray(b))
+
+
+# ---- kernel-level: tournament -----------------------------------------------------------------
+@pytest.mark.parametrize("n", [1, 7, 31, 32, 33, 511, 512, 513, 1024, 4097, 24576, 70000, 262144, 600000])
+def test_tournament_matches_oracle(S, n):
+    rng = np.random.default_rng(n)
+    with S.Solver() as s:
+        for kind in range(4):
+            if kind == 0:
+                v = rng.normal(size=n)
+            elif kind == 1:   # many exact ties at the minimum
+                v = np.where(rng.random(n) < 0.3, -1.0, rng.random(n))
+            elif kind == 2:   # epsilon ties (non-transitive region)
+                v = -1.0 + rng.integers(0, 5, size=n) * 4e-10
+            else:             # nothing below DBL_MAX
+                v = np.full(n, np.finfo(np.float64).max)
+            assert s.tournament(v) == O.tournament(v)
+
+
+# ---- generator ------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,m,lo,hi", [(256, 256, 1, 100), (37, 129, -100, 100), (1000, 64, 1, 100), (3, 700, -5, 5)])
+def test_generator_matches_oracle(S, n, m, lo, hi):
+    seeds = O.seed_triplet(n * 100 + m, 1)
+    A, b, c = O.generate(n, m, seeds, lo, hi)
+    with S.Solver() as s:
+        s.generate(n, m, seeds, lo, hi)
+        A2, b2, c2 = s.copy_problem()
+    assert same(A, A2) and same(b, b2) and same(c, c2)
+
+
+# ---- stepping parity: every intermediate state -----------------------------------------------------
+@pytest.mark.parametrize("fold", [True, False])
+@pytest.mark.parametrize("n,m,lo,hi,seed", [(24, 16, -100, 100, 3), (64, 64, 1, 100, 5), (100, 130, -100, 100, 9),
+                                            (600, 520, 1, 100, 11)])
+def test_stepping_bit_exact(S, fold, n, m, lo, hi, seed):
+    A, b, c = O.generate(n, m, O.seed_triplet(seed, 0), lo, hi)
+    o = O.Oracle(A, b, c)
+    with S.Solver(fold_artificials=fold, use_graph=False) as s:
+        s.load(A, b, c)
+        s.build_phase1(); o.build_phase1()
+        assert same(s.tableau(), o.tableau()) and same(s.costs(), o.costs()) and same(s.basis(), o.basis())
+        s.price_out(); o.priceout()
+        assert same(s.costs(), o.costs())
+        s.select_entering()
+        for k in range(40):
+            st_o = o.pivot()
+            st_s, done = s.iterate(1)
+            if st_o != O.CONTINUE:
+                assert st_s == st_o and done == 0
+                break
+            assert st_s in (S.RUNNING, S.FEASIBLE, S.UNBOUNDED) and done == 1
+            assert same(s.tableau(), o.tableau()), f"tableau differs after pivot {k}"
+            assert same(s.costs(), o.costs()), f"costs differ after pivot {k}"
+            assert same(s.basis(), o.basis())
+        # run the phase out and compare the switch
+        st_o = o.iterate(-1); st_s, _ = s.iterate(-1)
+        assert st_s == st_o
+        assert s.phase1_verdict() == o.phase1_verdict()
+        if o.phase1_verdict() == 0:
+            s.switch_phase2(); o.switch_phase2()
+            assert same(s.costs(), o.costs())
+            s.price_out(); o.priceout()
+            assert same(s.costs(), o.costs()) and same(s.tableau(), o.tableau())
+            s.select_entering()
+            st_o = o.iterate(-1); st_s, _ = s.iterate(-1)
+            assert st_s == st_o
+            assert same(s.tableau(), o.tableau()) and same(s.costs(), o.costs())
+            if st_o == 0:
+                xs, objs = s.extract(); xo, objo = o.extract()
+                assert same(xs, xo) and objs == objo
+        qp, cnt, h = s.trace()
+        assert same(qp, o.trace()) and h == o.hash()
+
+
+# ---- whole solves ----------------------------------------------------------------------------------
+def check_solve(S, A, b, c, rule=0, max_pivots=0, **opts):
+    r_o = O.Oracle(A, b, c, rule=rule).two_phase(max_pivots=max_pivots if max_pivots else -1)
+    with S.Solver(pivot_rule=rule, max_pivots=max_pivots, **opts) as s:
+        s.load(A, b, c)
+        r = s.solve()
+        qp, cnt, h = s.trace()
+    assert r["status"] == r_o["status"], (r["status"], r_o["status"])
+    assert same(qp, r_o["trace"]) and h == r_o["hash"]
+    assert (r["stats"].pivots_phase1, r["stats"].pivots_phase2) == tuple(r_o["pivots"])
+    assert same(r["basis"], r_o["basis"])
+    if r["status"] == 0:
+        assert r["objective"] == r_o["objective"] and same(r["x"], r_o["x"])
+    return r
+
+
+@pytest.mark.parametrize("name", ["smallProblem", "infeasibleProblem", "unboundedProblem"])
+def test_reference_examples(S, name):
+    ex = EXAMPLES[name]
+    p = S.readProblemFromFile(io.StringIO(ex["text"]))
+    r = check_solve(S, p.constraintsMatrix, p.knownTermsVector, p.objectiveFunction)
+    assert r["status"] == ex["status"]
+    status, x, obj = S.twoPhaseMethod(p)
+    assert status == ex["status"]
+    if status == 0:
+        assert obj == ex["objective"] and list(x) == ex["x"]
+
+
+def test_small_integer_suite_all_statuses(S):
+    from test_oracle_golden import small_integer_lps
+    seen = set()
+    for A, b, c in small_integer_lps(400):
+        seen.add(check_solve(S, A, b, c, max_pivots=1000, use_graph=False, batch=8)["status"])
+    assert {0, -1, -2, -3} <= seen
+
+
+@pytest.mark.parametrize("n,m", [(48, 32), (32, 48), (200, 100), (64, 512), (513, 1025)])
+def test_mixed_sign_suite(S, n, m):
+    for seed in range(1, 7):
+        A, b, c = O.generate(n, m, O.seed_triplet(seed, 0), -100, 100)
+        check_solve(S, A, b, c, max_pivots=200000)
+
+
+@pytest.mark.parametrize("rule", [1, 2])
+def test_alternative_pivot_rules(S, rule):
+    for n, m, lo in ((64, 64, 1), (48, 32, -100), (32, 48, -100), (300, 200, 1)):
+        for seed in (1, 2, 3):
+            A, b, c = O.generate(n, m, O.seed_triplet(seed, 1), lo, 100)
+            check_solve(S, A, b, c, rule=rule, max_pivots=500000)
+
+
+def test_blands_rule_breaks_cycling(S):
+    cases = json.load(open(os.path.join(HERE, "golden", "cycling.json")))["cases"]
+    for cs in cases:
+        A, b, c = np.array(cs["A"], float), np.array(cs["b"], float), np.array(cs["c"], float)
+        r = check_solve(S, A, b, c, rule=0, max_pivots=5000)   # cycles: both hit the cap identically
+        assert r["status"] == S.ITER_LIMIT
+        r = check_solve(S, A, b, c, rule=2, max_pivots=5000)
+        assert r["status"] == cs["bland_status"]
+
+
+@pytest.mark.parametrize("opts", [dict(fold_artificials=False), dict(skip_zero_rows=True), dict(use_graph=False),
+                                  dict(update_variant=2), dict(update_variant=4), dict(update_variant=1),
+                                  dict(batch=1), dict(update_variant=7, skip_zero_rows=True)])
+def test_options_do_not_change_results(S, opts):
+    A, b, c = O.generate(300, 260, O.seed_triplet(77, 1), 1, 100)
+    check_solve(S, A, b, c, **opts)
+    A, b, c = O.generate(90, 70, O.seed_triplet(5, 0), -100, 100)
+    check_solve(S, A, b, c, max_pivots=100000, **opts)
+
+
+# ---- published golden vectors at sizes the oracle needs minutes for --------------------------------
+def _grid(max_cons):
+    seen = set()
+    for inst in PUB["instances"]:
+        key = (inst["vars"], inst["constraints"], inst["seed"])
+        if inst["constraints"] <= max_cons and key not in seen and inst["phase2_ran"]:
+            seen.add(key)
+            yield inst
+
+
+@pytest.mark.parametrize("inst", list(_grid(2048)), ids=lambda i: f"{i['vars']}x{i['constraints']}")
+def test_published_grid(S, inst):
+    """Device-generated instance (MSVC seed flavour) -> published pivot counts of the reference, and the
+    oracle's pivot-sequence hash / objective from the committed fixture."""
+    n, m, seed = inst["vars"], inst["constraints"], inst["seed"]
+    with S.Solver() as s:
+        s.generate(n, m, S.seed_triplet(seed, S.RAND_MSVC), 1, 100)
+        r = s.solve()
+    assert r["status"] == 0
+    assert (r["stats"].pivots_phase1, r["stats"].pivots_phase2) == (inst["pivots_phase1"], inst["pivots_phase2"])
+    fx = ORC.get(f"{n}_{m}_{seed}")
+    if fx:
+        assert str(r["stats"].trace_hash) == fx["trace_hash"]
+        assert r["objective"] == fx["objective"]
+
+
+def test_false_infeasible_golden(S):
+    """The reference's 37th golden vector: 1024 x 8192, un-bumped seed 110592 -> INFEASIBLE after
+    exactly 14063 phase-1 pivots (data/measures/mx250_2/benchmark_1024_8192.txt)."""
+    with S.Solver() as s:
+        s.generate(1024, 8192, S.seed_triplet(110592, S.RAND_MSVC), 1, 100)
+        r = s.solve()
+    assert r["status"] == S.INFEASIBLE and r["stats"].pivots_phase1 == 14063
+
+
+# ---- size-independent properties at full size ------------------------------------------------------
+def test_full_size_properties(S):
+    """8192 x 8192 (the '8192x16384' tableau): 300 pivots, then invariants that hold for any correct
+    tableau: basic columns are unit vectors (up to the reference's own residuals), reduced costs of
+    basic variables vanish, and the objective equals c_B . b."""
+    n = m = 8192
+    with S.Solver() as s:
+        s.generate(n, m, S.seed_triplet(827392, S.RAND_MSVC), 1, 100)
+        s.build_phase1(); s.price_out(); s.select_entering()
+        st, done = s.iterate(300)
+        assert st == S.RUNNING and done == 300
+        costs = s.costs(); basis = s.basis()
+        qp, cnt, h = s.trace()
+        assert cnt == 300 and len(set(map(tuple, qp.tolist()))) == 300
+        assert np.all(np.abs(costs[1 + basis]) < 1e-6)
+        for i in np.flatnonzero(basis != (n + m + np.arange(m)))[:5]:
+            assert basis[i] == qp[qp[:, 1] == i][-1, 0]
