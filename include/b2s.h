@@ -64,7 +64,7 @@ typedef struct b2s_options {
     int batch;            /* pivots enqueued between two host status polls; 0 = choose from size     */
     long long max_pivots; /* total pivot cap for b2s_solve_two_phase; <= 0 = none (as the reference) */
     long long trace_capacity; /* (q,p) pairs kept on the device for b2s_copy_trace; 0 = default 1<<20 */
-    int update_variant;   /* rank-1 update kernel variant (0 = default); for tuning/benchmarks       */
+    int update_variant;   /* rank-1 update kernel variant (default 4: 256-bit accesses, 8 rows in flight) */
     int reserved[7];
 } b2s_options;
 
@@ -120,7 +120,8 @@ int b2s_select_entering(b2s_solver *s); /* minElement(costs+1,...), src/solver.c
  * *status: B2S_RUNNING when the budget ran out first, else FEASIBLE (phase optimal) / UNBOUNDED. */
 int b2s_iterate(b2s_solver *s, long long max_pivots, int *status, long long *pivots_done);
 int b2s_phase1_verdict(b2s_solver *s, int *status); /* src/twoPhaseMethod.cu:258-282             */
-int b2s_switch_phase2(b2s_solver *s);               /* src/twoPhaseMethod.cu:285-337 (incl. price-out + select) */
+int b2s_switch_phase2(b2s_solver *s);               /* src/twoPhaseMethod.cu:285-318: drop artificials, load -c;
+                                                       follow with b2s_price_out + b2s_select_entering        */
 int b2s_extract_solution(b2s_solver *s, double *x, double *objective); /* :370-383               */
 
 /* ---- introspection ------------------------------------------------------------------------ */
@@ -143,6 +144,13 @@ int b2s_tournament(b2s_solver *s, const double *vec, long long n, double *value,
  * event times measured on the solver's stream; flush_l2 != 0 rewrites a >L2 buffer between
  * launches.  *bytes_per_launch = 2 * rows_stored * m * sizeof(real). */
 int b2s_bench_update(b2s_solver *s, int launches, int flush_l2, float *ms_each, double *bytes_per_launch);
+
+/* `count` real pivots of the current phase launched one kernel at a time with CUDA events between
+ * the three launches of each pivot (ratio test / gather+normalise / fused rank-1 update); the
+ * arrays receive per-pivot kernel times in ms.  This is how bench.py measures the update kernel's
+ * share and its achieved HBM bandwidth on live data. */
+int b2s_profile_pivots(b2s_solver *s, int count, float *ms_ratio, float *ms_gather, float *ms_update,
+                       long long *pivots_done);
 
 /* ---- sharded solves (constraint slabs over the GPUs of one box) ------------------------------ */
 #define B2S_NCCL_ID_BYTES 128

@@ -20,7 +20,22 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "_ref", "libsimplex_ref.so")
 
 
+def generate():
+    """python oracle/ref_runner.py --generate <vars> <cons> <seed> <min> <max> <out.npz>: the reference's
+    own generateRandomProblem (glibc rand() seeds, cuRAND XORWOW kernels)."""
+    n, m, seed, lo, hi = (int(v) for v in sys.argv[2:7])
+    lib = C.CDLL(LIB)
+    dp = C.POINTER(C.c_double)
+    lib.ref_generate.argtypes = [C.c_int, C.c_int, C.c_uint, C.c_int, C.c_int, dp, dp, dp]
+    lib.ref_setup_device()
+    A = np.zeros((n, m)); b = np.zeros(m); c = np.zeros(n)
+    lib.ref_generate(n, m, seed, lo, hi, A.ctypes.data_as(dp), b.ctypes.data_as(dp), c.ctypes.data_as(dp))
+    np.savez(sys.argv[7], A=A, b=b, c=c)
+
+
 def main():
+    if sys.argv[1] == "--generate":
+        return generate()
     prob, out = sys.argv[1], sys.argv[2]
     trace_on = "--trace" in sys.argv[3:]
     z = np.load(prob)

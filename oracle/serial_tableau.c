@@ -565,7 +565,7 @@ void orc_xorwow_outputs(uint64_t seed, uint64_t offset, long count, uint32_t *ou
 
 /* ------------------------------------------------------------------------------------------
  * CLI: serial_tableau <n> <m> <seed> <lo> <hi> <flavour> <rule> <threads> <max_pivots>
- * Prints one line: status pivots1 pivots2 objective hash seconds.  Used by bench.py's
+ * Prints one line: status pivots1 pivots2 objective hash seconds_total seconds_in_pivot_loops.  Used by bench.py's
  * cpu_baseline leg (bounded pivot budget) and by hand.
  * ---------------------------------------------------------------------------------------- */
 #ifdef ORC_MAIN
@@ -593,11 +593,29 @@ int main(int argc, char **argv)
     double *x = malloc(sizeof(double) * n), obj = 0;
     orc_generate(n, m, seeds, lo, hi, A, b, c);
     orc_t *o = orc_create(n, m, A, b, c, rule, threads);
-    double t0 = now_s();
-    int st = orc_two_phase(o, maxp, x, &obj);
+    double t0 = now_s(), loop = 0.0, t;
+    /* same sequence as orc_two_phase, with the pivot loops timed on their own */
+    orc_build_phase1(o);
+    orc_priceout(o);
+    t = now_s();
+    int st = orc_iterate(o, maxp);
+    loop += now_s() - t;
+    if (st == ORC_CONTINUE) {
+        st = ORC_ITER_LIMIT;
+    } else if ((st = orc_phase1_verdict(o)) == ORC_FEASIBLE) {
+        orc_switch_phase2(o);
+        orc_priceout(o);
+        t = now_s();
+        st = orc_iterate(o, maxp < 0 ? -1 : maxp - o->pivots[0]);
+        loop += now_s() - t;
+        if (st == ORC_CONTINUE)
+            st = ORC_ITER_LIMIT;
+        else if (st == ORC_FEASIBLE)
+            orc_extract(o, x, &obj);
+    }
     double t1 = now_s();
-    printf("%d %ld %ld %.17g %llu %.6f\n", st, o->pivots[0], o->pivots[1], st == 0 ? obj : o->cost[0],
-           (unsigned long long)o->hash, t1 - t0);
+    printf("%d %ld %ld %.17g %llu %.6f %.6f\n", st, o->pivots[0], o->pivots[1], st == 0 ? obj : o->cost[0],
+           (unsigned long long)o->hash, t1 - t0, loop);
     return 0;
 }
 #endif

@@ -49,6 +49,7 @@ struct SolverBase {
     virtual int tournament(const double* vec, long long n, double* value, int* index) = 0;
     virtual int bench_update(int launches, int flush, float* ms, double* bytes) = 0;
     virtual int dist_init(int rank, int world, const char* id) = 0;
+    virtual int profile_pivots(int count, float* ms_ratio, float* ms_gather, float* ms_update, long long* done) = 0;
 
     int fail(int code, const char* fmt, ...)
     {
@@ -109,7 +110,8 @@ struct SolverImpl final : SolverBase {
     double* stage_dev = nullptr;  // fp64 staging for fp32 loads / exports
     size_t cap_stage = 0;
     DevState* st = nullptr;
-    DevState* st_host = nullptr;  // pinned
+    DevState* st_host = nullptr;  // pinned, [0] = current snapshot, [1..2] = pipelined poll slots
+    cudaEvent_t poll_ev[2] = {nullptr, nullptr};
     int2* trace = nullptr;
     long long trace_cap = 0;
     uint32_t* jump_tables = nullptr;
@@ -145,6 +147,10 @@ struct SolverImpl final : SolverBase {
         cudaFree(verdict);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
+        for (auto& e : poll_ev) {
+            if (e) cudaEventDestroy(e);
+            e = nullptr;
+        }
         if (stream) cudaStreamDestroy(stream);
 #ifdef B2S_WITH_NCCL
         if (comm) ncclCommDestroy(comm);
@@ -201,7 +207,9 @@ struct SolverImpl final : SolverBase {
         CK(cudaEventCreate(&ev1));
         CK(cudaMalloc(&st, sizeof(DevState)));
         CK(cudaMemset(st, 0, sizeof(DevState)));
-        CK(cudaHostAlloc(&st_host, sizeof(DevState), cudaHostAllocDefault));
+        CK(cudaHostAlloc(&st_host, 3 * sizeof(DevState), cudaHostAllocDefault));
+        CK(cudaEventCreateWithFlags(&poll_ev[0], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&poll_ev[1], cudaEventDisableTiming));
         CK(cudaMalloc(&verdict, 2 * sizeof(int)));
         trace_cap = opt.trace_capacity > 0 ? opt.trace_capacity : (1ll << 20);
         CK(cudaMalloc(&trace, sizeof(int2) * (size_t)trace_cap));
@@ -637,15 +645,37 @@ struct SolverImpl final : SolverBase {
         const long long limit = max_pivots < 0 ? LLONG_MAX : start + max_pivots;
         CK(cudaMemcpyAsync(&st->limit, &limit, sizeof(long long), cudaMemcpyHostToDevice, stream));
         CK(cudaEventRecord(ev0, stream));
+        // Batches are enqueued one ahead of the status poll, so the device never idles while the host
+        // looks at the state; a batch enqueued after the phase ended (or the budget ran out) costs only
+        // its early-exit launches because every kernel checks the device-resident status/limit first.
         const int full = pick_batch();
-        while (true) {
-            const long long left = limit - st_host->pivots;
+        const bool graphable = opt.use_graph && world == 1;
+        long long enq = 0;  // pivots enqueued so far (upper bound on pivots made)
+        auto enqueue = [&](int slot) -> int {
+            long long left = limit - start - enq;
             int batch = full;
-            if (!(opt.use_graph && world == 1) && left < batch) batch = (int)left;
-            if ((rc = launch_batch(batch))) return rc;
-            if ((rc = fetch_state())) return rc;
-            if (st_host->status != kRunning || st_host->pivots >= limit) break;
+            if (!graphable && left < batch) batch = (int)std::max<long long>(left, 1);
+            int rc2 = launch_batch(batch);
+            if (rc2) return rc2;
+            enq += batch;
+            CK(cudaMemcpyAsync(st_host + 1 + slot, st, sizeof(DevState), cudaMemcpyDeviceToHost, stream));
+            CK(cudaEventRecord(poll_ev[slot], stream));
+            return B2S_OK;
+        };
+        int slot = 0;
+        if ((rc = enqueue(slot))) return rc;
+        while (true) {
+            const bool more = (limit == LLONG_MAX) || (start + enq < limit);
+            if (more && (rc = enqueue(slot ^ 1))) return rc;
+            CK(cudaEventSynchronize(poll_ev[slot]));
+            const DevState& snap = st_host[1 + slot];
+            if (snap.status != kRunning || snap.pivots >= limit) break;
+            if (!more) {  // budget fully enqueued but not yet consumed: cannot happen (limit enforced on device)
+                break;
+            }
+            slot ^= 1;
         }
+        if ((rc = fetch_state())) return rc;
         CK(cudaEventRecord(ev1, stream));
         CK(cudaEventSynchronize(ev1));
         float ms = 0;
@@ -900,6 +930,44 @@ struct SolverImpl final : SolverBase {
         return B2S_OK;
     }
 
+    // Real pivots, launched one kernel at a time with CUDA events between the three launches.
+    int profile_pivots(int count, float* ms_ratio, float* ms_gather, float* ms_update, long long* done) override
+    {
+        if (stage != kReady) return fail(B2S_ERR_STATE, "profile_pivots follows select_entering / iterate");
+        if (world > 1) return fail(B2S_ERR_STATE, "profile_pivots is single-GPU only");
+        CK(cudaSetDevice(dev));
+        int rc = fetch_state();
+        if (rc) return rc;
+        const long long start = st_host->pivots;
+        const long long limit = start + count;
+        CK(cudaMemcpyAsync(&st->limit, &limit, sizeof(long long), cudaMemcpyHostToDevice, stream));
+        std::vector<cudaEvent_t> ev(4 * (size_t)count);
+        for (auto& e : ev) CK(cudaEventCreate(&e));
+        const long long work = std::max(Rs, ld);
+        for (int k = 0; k < count; ++k) {
+            CK(cudaEventRecord(ev[4 * k + 0], stream));
+            ratio_kernel<real, false><<<P.Gm, kSelBlock, 0, stream>>>(P);
+            CK(cudaEventRecord(ev[4 * k + 1], stream));
+            gather_kernel<real, false><<<(unsigned)((work + 255) / 256), 256, 0, stream>>>(P);
+            CK(cudaEventRecord(ev[4 * k + 2], stream));
+            update_fn()<<<upd_grid, kSelBlock, 0, stream>>>(P);
+            CK(cudaEventRecord(ev[4 * k + 3], stream));
+        }
+        CK(cudaGetLastError());
+        if ((rc = fetch_state())) return rc;
+        for (int k = 0; k < count; ++k) {
+            CK(cudaEventElapsedTime(ms_ratio + k, ev[4 * k + 0], ev[4 * k + 1]));
+            CK(cudaEventElapsedTime(ms_gather + k, ev[4 * k + 1], ev[4 * k + 2]));
+            CK(cudaEventElapsedTime(ms_update + k, ev[4 * k + 2], ev[4 * k + 3]));
+        }
+        for (auto& e : ev) cudaEventDestroy(e);
+        const long long made = st_host->pivots - start;
+        if (phase == 2) pivots_p2 += made; else pivots_p1 += made;
+        if (done) *done = made;
+        if (st_host->status != kRunning) stage = kPhaseDone;
+        return B2S_OK;
+    }
+
     int dist_init(int rank_, int world_, const char* id) override
     {
 #ifdef B2S_WITH_NCCL
@@ -954,7 +1022,7 @@ void b2s_default_options(b2s_options* opt)
     opt->batch = 0;
     opt->max_pivots = 0;
     opt->trace_capacity = 0;
-    opt->update_variant = 0;
+    opt->update_variant = 4;
 }
 
 int b2s_device_count(void)
@@ -1050,6 +1118,11 @@ int b2s_bench_update(b2s_solver* s, int launches, int flush_l2, float* ms_each, 
     B2S_FWD(bench_update(launches, flush_l2, ms_each, bytes_per_launch));
 }
 int b2s_dist_init(b2s_solver* s, int rank, int world, const char id[B2S_NCCL_ID_BYTES]) { B2S_FWD(dist_init(rank, world, id)); }
+int b2s_profile_pivots(b2s_solver* s, int count, float* ms_ratio, float* ms_gather, float* ms_update, long long* pivots_done)
+{
+    if (count < 1 || !ms_ratio || !ms_gather || !ms_update) return B2S_ERR_ARG;
+    B2S_FWD(profile_pivots(count, ms_ratio, ms_gather, ms_update, pivots_done));
+}
 
 int b2s_dist_unique_id(char id[B2S_NCCL_ID_BYTES])
 {

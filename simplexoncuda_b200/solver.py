@@ -30,7 +30,7 @@ class Solver:
 
     def __init__(self, device=0, dtype=L.F64, pivot_rule=L.RULE_REFERENCE, fold_artificials=True,
                  skip_zero_rows=False, use_graph=True, batch=0, max_pivots=0, trace_capacity=0,
-                 update_variant=0):
+                 update_variant=4):
         self.lib = L.load()
         opt = L.Options()
         self.lib.b2s_default_options(C.byref(opt))
@@ -173,6 +173,13 @@ class Solver:
         ms = (C.c_float * launches)(); nbytes = C.c_double()
         self._ck(self.lib.b2s_bench_update(self.h, launches, int(flush_l2), ms, C.byref(nbytes)))
         return np.array(list(ms), dtype=np.float64), nbytes.value
+
+    def profile_pivots(self, count):
+        """`count` real pivots with per-kernel CUDA-event times: dict of ms arrays + pivots made."""
+        a = (C.c_float * count)(); b = (C.c_float * count)(); u = (C.c_float * count)(); done = C.c_longlong()
+        self._ck(self.lib.b2s_profile_pivots(self.h, count, a, b, u, C.byref(done)))
+        k = done.value
+        return {"ratio_ms": np.array(a[:k]), "gather_ms": np.array(b[:k]), "update_ms": np.array(u[:k]), "pivots": k}
 
     # ---- sharding --------------------------------------------------------------------------------
     def dist_init(self, rank, world, unique_id):
