@@ -55,7 +55,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-pivots", type=int, default=0, help="pivot budget of the cpu_baseline sample (0 = auto)")
     ap.add_argument("--skip-zero-rows", action="store_true")
-    ap.add_argument("--update-variant", type=int, default=4)
+    ap.add_argument("--update-variant", type=int, default=8)
     return ap.parse_args()
 
 

@@ -64,7 +64,8 @@ typedef struct b2s_options {
     int batch;            /* pivots enqueued between two host status polls; 0 = choose from size     */
     long long max_pivots; /* total pivot cap for b2s_solve_two_phase; <= 0 = none (as the reference) */
     long long trace_capacity; /* (q,p) pairs kept on the device for b2s_copy_trace; 0 = default 1<<20 */
-    int update_variant;   /* rank-1 update kernel variant (default 4: 256-bit accesses, 8 rows in flight) */
+    int update_variant;   /* rank-1 update kernel variant (default 8: 256-bit accesses, 8 rows in flight,
+                             device-wide ticket scheduler over 8-row tiles); others exist for tuning  */
     int reserved[7];
 } b2s_options;
 

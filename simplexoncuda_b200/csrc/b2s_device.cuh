@@ -47,6 +47,8 @@ struct DevState {
     long long rows_streamed; // statistics
     long long rows_total;
     int any_negated;
+    unsigned int tile_ticket;  // dynamic tile scheduler of the update kernel
+    unsigned int tile_done;
     int pad;
 };
 

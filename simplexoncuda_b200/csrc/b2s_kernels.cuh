@@ -355,12 +355,13 @@ __global__ void __launch_bounds__(256) svec_kernel(PivotParams<real> P)
 // registers) and walks rows in unrolled groups of U independent 128/256-bit loads.  The first Gc
 // CTAs first update the cost vector and run the next pivot's entering-column tournament.
 // ---------------------------------------------------------------------------------------------
-template <typename real, int VB, int U, int HINT, bool SKIP>
+template <typename real, int VB, int U, int HINT, bool SKIP, bool DYN>
 __global__ void __launch_bounds__(kSelBlock, (VB * U <= 128) ? 2 : 1) update_kernel(PivotParams<real> P)
 {
     constexpr int EPT = VB / (int)sizeof(real);
     __shared__ TreeSmem<real> sm;
     __shared__ int s_flag;
+    __shared__ long long s_next;
     if (!__ldcg(&P.st->live)) return;
 
     if (blockIdx.x < P.Gc) cost_select_blocks<real, true>(P, sm, &s_flag);
@@ -372,39 +373,65 @@ __global__ void __launch_bounds__(kSelBlock, (VB * U <= 128) ? 2 : 1) update_ker
     const long long chunk_cols = (long long)EPT << P.log2_tpr;
     int cur_chunk = -1;
     real sreg[EPT];
-    for (long long tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
+    // Tiles are handed out either statically (tile += gridDim) or, DYN, by a device-wide ticket
+    // counter fetched one tile ahead, so SMs that stream faster simply take more tiles and the
+    // whole grid walks the tableau as one compact address window.
+    long long tile = blockIdx.x;
+    while (tile < P.ntiles) {
+        if (DYN && threadIdx.x == 0)
+            s_next = (long long)atomicAdd(&P.st->tile_ticket, 1u) + gridDim.x;
         const int chunk = (int)(tile % P.nchunks);
         const long long rb = tile / P.nchunks;
         const long long c = chunk * chunk_cols + (long long)tx * EPT;
-        if (c >= P.ld) continue;
-        if (chunk != cur_chunk) {
-            cur_chunk = chunk;
+        if (c < P.ld) {
+            if (chunk != cur_chunk) {
+                cur_chunk = chunk;
 #pragma unroll
-            for (int e = 0; e < EPT; ++e) sreg[e] = __ldg(P.s + c + e);
-        }
-        const long long r0 = rb * tile_rows + ty;
-        for (int g = 0; g < P.tile_groups; ++g) {
-            real a[U];
-            Pack<VB>* ptr[U];
-            PackView<real, VB> v[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const long long r = r0 + (long long)(g * U + u) * rpp;
-                a[u] = (r < P.Rs) ? __ldg(P.rowp + r) : (real)0;
-                ptr[u] = reinterpret_cast<Pack<VB>*>(P.T + r * P.ld + c);
-                if (!SKIP && !(r < P.Rs)) ptr[u] = nullptr;
-                if (SKIP && a[u] == (real)0) ptr[u] = nullptr;
+                for (int e = 0; e < EPT; ++e) sreg[e] = __ldg(P.s + c + e);
             }
+            const long long r0 = rb * tile_rows + ty;
+            for (int g = 0; g < P.tile_groups; ++g) {
+                real a[U];
+                Pack<VB>* ptr[U];
+                PackView<real, VB> v[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u)
-                if (ptr[u]) v[u].p = ld_pack<HINT>(ptr[u]);
-#pragma unroll
-            for (int u = 0; u < U; ++u)
-                if (ptr[u]) {
-#pragma unroll
-                    for (int e = 0; e < EPT; ++e) v[u].e[e] = fma_r(sreg[e], a[u], v[u].e[e]);
-                    st_pack<HINT>(ptr[u], v[u].p);
+                for (int u = 0; u < U; ++u) {
+                    const long long r = r0 + (long long)(g * U + u) * rpp;
+                    a[u] = (r < P.Rs) ? __ldg(P.rowp + r) : (real)0;
+                    ptr[u] = reinterpret_cast<Pack<VB>*>(P.T + r * P.ld + c);
+                    if (!SKIP && !(r < P.Rs)) ptr[u] = nullptr;
+                    if (SKIP && a[u] == (real)0) ptr[u] = nullptr;
                 }
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    if (ptr[u]) v[u].p = ld_pack<HINT>(ptr[u]);
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    if (ptr[u]) {
+#pragma unroll
+                        for (int e = 0; e < EPT; ++e) v[u].e[e] = fma_r(sreg[e], a[u], v[u].e[e]);
+                        st_pack<HINT>(ptr[u], v[u].p);
+                    }
+            }
+        }
+        if (DYN) {
+            __syncthreads();
+            tile = s_next;
+            __syncthreads();
+        } else {
+            tile += gridDim.x;
+        }
+    }
+    if (DYN) {
+        // the last CTA to leave re-arms the ticket counters for the next launch
+        if (threadIdx.x == 0) {
+            __threadfence();
+            const unsigned done = atomicAdd(&P.st->tile_done, 1u);
+            if (done == gridDim.x - 1) {
+                P.st->tile_ticket = 0;
+                P.st->tile_done = 0;
+                __threadfence();
+            }
         }
     }
 }

@@ -290,35 +290,45 @@ struct SolverImpl final : SolverBase {
 
     // ---- update-kernel variants --------------------------------------------------------------
     struct Variant {
-        int vb, u, hint;
+        int vb, u, hint, dyn;
     };
+    static constexpr int kNumVariants = 14;
     Variant variant() const
     {
-        static const Variant table[] = {{16, 8, 0}, {16, 8, 1}, {32, 4, 0}, {32, 4, 1},
-                                        {32, 8, 0}, {16, 4, 0}, {16, 8, 2}, {32, 8, 1}};
+        static const Variant table[kNumVariants] = {{16, 8, 0, 0}, {16, 8, 1, 0}, {32, 4, 0, 0}, {32, 4, 1, 0}, {32, 8, 0, 0},
+                                                    {16, 4, 0, 0}, {16, 8, 2, 0}, {32, 8, 1, 0}, {32, 8, 0, 1}, {32, 4, 0, 1},
+                                                    {16, 4, 0, 1}, {32, 8, 1, 1}, {32, 8, 2, 1}, {16, 8, 0, 1}};
         int v = opt.update_variant;
-        if (v < 0 || v >= (int)(sizeof(table) / sizeof(table[0]))) v = 0;
+        if (v < 0 || v >= kNumVariants) v = 8;
         return table[v];
     }
     typedef void (*UpdateFn)(PivotParams<real>);
-    template <int VB, int U, int HINT>
+    template <int VB, int U, int HINT, bool DYN>
     UpdateFn pick_skip() const
     {
-        return opt.skip_zero_rows ? (UpdateFn)update_kernel<real, VB, U, HINT, true>
-                                  : (UpdateFn)update_kernel<real, VB, U, HINT, false>;
+        return opt.skip_zero_rows ? (UpdateFn)update_kernel<real, VB, U, HINT, true, DYN>
+                                  : (UpdateFn)update_kernel<real, VB, U, HINT, false, DYN>;
     }
     UpdateFn update_fn() const
     {
-        switch (std::min(std::max(opt.update_variant, 0), 7)) {
+        int v = opt.update_variant;
+        if (v < 0 || v >= kNumVariants) v = 8;
+        switch (v) {
+            case 0: return pick_skip<16, 8, 0, false>();
+            case 1: return pick_skip<16, 8, 1, false>();
+            case 2: return pick_skip<32, 4, 0, false>();
+            case 3: return pick_skip<32, 4, 1, false>();
+            case 4: return pick_skip<32, 8, 0, false>();
+            case 5: return pick_skip<16, 4, 0, false>();
+            case 6: return pick_skip<16, 8, 2, false>();
+            case 7: return pick_skip<32, 8, 1, false>();
             default:
-            case 0: return pick_skip<16, 8, 0>();
-            case 1: return pick_skip<16, 8, 1>();
-            case 2: return pick_skip<32, 4, 0>();
-            case 3: return pick_skip<32, 4, 1>();
-            case 4: return pick_skip<32, 8, 0>();
-            case 5: return pick_skip<16, 4, 0>();
-            case 6: return pick_skip<16, 8, 2>();
-            case 7: return pick_skip<32, 8, 1>();
+            case 8: return pick_skip<32, 8, 0, true>();
+            case 9: return pick_skip<32, 4, 0, true>();
+            case 10: return pick_skip<16, 4, 0, true>();
+            case 11: return pick_skip<32, 8, 1, true>();
+            case 12: return pick_skip<32, 8, 2, true>();
+            case 13: return pick_skip<16, 8, 0, true>();
         }
     }
 
@@ -372,8 +382,10 @@ struct SolverImpl final : SolverBase {
         for (; tg > 1; tg >>= 1) {
             const long long rows_tile = (long long)rpp * v.u * tg;
             const long long nt = ((Rs + rows_tile - 1) / rows_tile) * P.nchunks;
-            if (nt >= 4ll * grid) break;
+            if (nt >= (v.dyn ? 16ll : 4ll) * grid) break;
         }
+        if (v.dyn) tg = 1;  // finest tiles: measured best with the ticket scheduler (profiles/r01_kernel_sweep.md)
+        if (const char* e = getenv("B2S_TILE_GROUPS")) tg = std::max(1, atoi(e));
         P.tile_groups = tg;
         const long long rows_tile = (long long)rpp * v.u * tg;
         P.ntiles = ((Rs + rows_tile - 1) / rows_tile) * P.nchunks;
@@ -1022,7 +1034,7 @@ void b2s_default_options(b2s_options* opt)
     opt->batch = 0;
     opt->max_pivots = 0;
     opt->trace_capacity = 0;
-    opt->update_variant = 4;
+    opt->update_variant = 8;
 }
 
 int b2s_device_count(void)

@@ -30,7 +30,7 @@ class Solver:
 
     def __init__(self, device=0, dtype=L.F64, pivot_rule=L.RULE_REFERENCE, fold_artificials=True,
                  skip_zero_rows=False, use_graph=True, batch=0, max_pivots=0, trace_capacity=0,
-                 update_variant=4):
+                 update_variant=8):
         self.lib = L.load()
         opt = L.Options()
         self.lib.b2s_default_options(C.byref(opt))
