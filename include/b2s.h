@@ -146,6 +146,22 @@ int b2s_tournament(b2s_solver *s, const double *vec, long long n, double *value,
  * launches.  *bytes_per_launch = 2 * rows_stored * m * sizeof(real). */
 int b2s_bench_update(b2s_solver *s, int launches, int flush_l2, float *ms_each, double *bytes_per_launch);
 
+/* ---- caller-owned tableau: the reference's tabular_t level (include/tabular.cuh:5-30) ------------ */
+/* Point the solver at a device tableau the caller allocated in the reference layout (pitched rows,
+ * rows_active x cols, separate cost vector of rows_active entries; no folding).  This is what
+ * `int solve(tabular_t*, int* base)` (include/solver.h:26) and `updateObjectiveFunction(tabular_t*,
+ * int*)` (include/gaussian.cuh:5) are implemented with: attach, b2s_set_basis, then
+ * b2s_price_out / b2s_select_entering + b2s_iterate, then b2s_copy_basis.  fp64 solvers only. */
+int b2s_attach_tableau_device(b2s_solver *s, double *table, size_t pitch_bytes, int rows_active, int cols,
+                              double *costs, int n_vars);
+int b2s_set_basis(b2s_solver *s, const int *basis_host); /* m entries */
+/* minElement(g_vet,size,&idx) (include/reduction.cuh:12), minElement(knownTerms,rowPivot,size,&idx)
+ * (:14) and isLessOrEqualThanZero (:23) on DEVICE vectors, reference semantics bit for bit. */
+int b2s_min_element_device(b2s_solver *s, const double *dvec, long long n, double *value, unsigned *index);
+int b2s_ratio_min_device(b2s_solver *s, const double *known_terms, const double *column, long long n, double *value,
+                         unsigned *index);
+int b2s_max_le_zero_device(b2s_solver *s, const double *dvec, long long n, int *result);
+
 /* `count` real pivots of the current phase launched one kernel at a time with CUDA events between
  * the three launches of each pivot (ratio test / gather+normalise / fused rank-1 update); the
  * arrays receive per-pivot kernel times in ms.  This is how bench.py measures the update kernel's

@@ -22,4 +22,11 @@ cd "$REF"
     main.cu $SRCS src/solver.cu src/chrono.cu
 "$NVCC" -rdc=true -shared -Xcompiler -fPIC -o "$OUT/libsimplex_ref.so" -Iinclude/ -I"$REF" -arch=sm_100 -w \
     $SRCS "$HERE/ref_shim.cu"
-echo "built $OUT/SimplexOnCuda_ref and $OUT/libsimplex_ref.so"
+# Drop-in proof: the reference's own, unmodified main.cu compiled against OUR headers (include/compat)
+# and linked against OUR libraries instead of the reference's sources.
+LIBDIR="$HERE/../simplexoncuda_b200/lib"
+if [ -f "$LIBDIR/libb2s_compat.so" ]; then
+    "$NVCC" -arch=sm_100 -w -D TIMER -I"$HERE/../include/compat" -o "$OUT/SimplexOnCuda_dropin" main.cu \
+        -L"$LIBDIR" -lb2s_compat -lb2s -Xlinker -rpath,"$LIBDIR"
+fi
+echo "built $OUT/SimplexOnCuda_ref, $OUT/libsimplex_ref.so, $OUT/SimplexOnCuda_dropin"

@@ -68,6 +68,11 @@ SIGNATURES = {
     "b2s_get_stats": (C.c_int, [_P, C.POINTER(Stats)]),
     "b2s_tournament": (C.c_int, [_P, _D, C.c_longlong, _D, _I]),
     "b2s_bench_update": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_float), _D]),
+    "b2s_attach_tableau_device": (C.c_int, [_P, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_int]),
+    "b2s_set_basis": (C.c_int, [_P, _I]),
+    "b2s_min_element_device": (C.c_int, [_P, C.c_void_p, C.c_longlong, _D, C.POINTER(C.c_uint)]),
+    "b2s_ratio_min_device": (C.c_int, [_P, C.c_void_p, C.c_void_p, C.c_longlong, _D, C.POINTER(C.c_uint)]),
+    "b2s_max_le_zero_device": (C.c_int, [_P, C.c_void_p, C.c_longlong, _I]),
     "b2s_profile_pivots": (C.c_int, [_P, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), _LL]),
     "b2s_dist_unique_id": (C.c_int, [C.c_char_p]),
     "b2s_dist_init": (C.c_int, [_P, C.c_int, C.c_int, C.c_char_p]),

@@ -576,6 +576,24 @@ __global__ void __launch_bounds__(256) bench_fill_kernel(PivotParams<real> P)
     }
 }
 
+// Stand-alone vector primitives behind the reference's reduction.cuh entry points.
+template <typename real>
+__global__ void __launch_bounds__(256) ratio_vector_kernel(const real* __restrict__ known, const real* __restrict__ column,
+                                                          long long n, real* out)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (cmp3((double)column[i], 0.0) > 0) ? div_r(known[i], column[i]) : Limits<real>::big();  // src/reduction.cu:106-114
+}
+template <typename real>
+__global__ void __launch_bounds__(kSelBlock) max_vector_kernel(const real* __restrict__ v, long long n, real* out)
+{
+    __shared__ real smax[32];
+    real mx = Limits<real>::tiny();  // src/reduction.cu:171
+    for (long long i = threadIdx.x; i < n; i += kSelBlock) mx = fmax(mx, v[i]);
+    mx = block_max_512(mx, smax);
+    if (threadIdx.x == 0) *out = mx;
+}
+
 // Loop-state (re)initialisation: fresh = 1 at build (counters and hash restart), 0 at the phase switch.
 __global__ void state_reset_kernel(DevState* st, int fresh)
 {

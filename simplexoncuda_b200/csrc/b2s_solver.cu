@@ -47,6 +47,11 @@ struct SolverBase {
     virtual int copy_trace(int* qp, long long cap, long long* len, unsigned long long* hash) = 0;
     virtual int get_stats(b2s_stats* st) = 0;
     virtual int tournament(const double* vec, long long n, double* value, int* index) = 0;
+    virtual int attach(double* table, size_t pitch, int rows, int cols, double* costs, int n_vars) = 0;
+    virtual int set_basis(const int* base_host) = 0;
+    virtual int min_element_device(const double* dvec, long long n, double* value, unsigned* index) = 0;
+    virtual int ratio_min_device(const double* known, const double* column, long long n, double* value, unsigned* index) = 0;
+    virtual int max_le_zero_device(const double* dvec, long long n, int* result) = 0;
     virtual int bench_update(int launches, int flush, float* ms, double* bytes) = 0;
     virtual int dist_init(int rank, int world, const char* id) = 0;
     virtual int profile_pivots(int count, float* ms_ratio, float* ms_gather, float* ms_update, long long* done) = 0;
@@ -101,7 +106,9 @@ struct SolverImpl final : SolverBase {
     int phase = 0;
     Stage stage = kEmpty;
     bool folded = true;
+    bool attached = false;  // T / cost alias a caller-owned tabular_t (reference layout, no folding)
 
+    real *T_own = nullptr, *cost_own = nullptr;  // allocations; T / cost may instead alias a caller's tabular_t
     real *T = nullptr, *cost = nullptr, *col = nullptr, *s = nullptr, *rowp = nullptr, *coef = nullptr, *c_dev = nullptr;
     real *rslot_v = nullptr, *rslot_max = nullptr, *cslot_v = nullptr;
     int *rslot_i = nullptr, *rslot_k = nullptr, *cslot_i = nullptr, *cslot_k = nullptr;
@@ -168,8 +175,9 @@ struct SolverImpl final : SolverBase {
 
     void free_problem()
     {
-        cudaFree(T);
-        cudaFree(cost);
+        cudaFree(T_own);
+        cudaFree(cost_own);
+        T_own = cost_own = nullptr;
         cudaFree(col);
         cudaFree(s);
         cudaFree(rowp);
@@ -244,8 +252,8 @@ struct SolverImpl final : SolverBase {
         if (needT > cap_T || (size_t)R1 > cap_rows || (size_t)ld > cap_cols || (size_t)n > cap_n) {
             free_problem();
             int rc;
-            if ((rc = dmalloc(&T, needT))) return rc;
-            if ((rc = dmalloc(&cost, (size_t)R1))) return rc;
+            if ((rc = dmalloc(&T_own, needT))) return rc;
+            if ((rc = dmalloc(&cost_own, (size_t)R1))) return rc;
             if ((rc = dmalloc(&rowp, (size_t)R1))) return rc;
             if ((rc = dmalloc(&col, (size_t)ld))) return rc;
             if ((rc = dmalloc(&s, (size_t)ld))) return rc;
@@ -266,6 +274,9 @@ struct SolverImpl final : SolverBase {
             cap_cols = (size_t)ld;
             cap_n = (size_t)n;
         }
+        T = T_own;
+        cost = cost_own;
+        attached = false;
         CK(cudaMemsetAsync(st, 0, sizeof(DevState), stream));
         pivots_p1 = pivots_p2 = 0;
         sec_load = sec_p1 = sec_p2 = 0;
@@ -554,7 +565,8 @@ struct SolverImpl final : SolverBase {
 
     int select_entering() override
     {
-        if (stage != kPriced) return fail(B2S_ERR_STATE, "select_entering follows price_out");
+        if (stage != kPriced && !(attached && stage == kBuilt))
+            return fail(B2S_ERR_STATE, "select_entering follows price_out");
         CK(cudaSetDevice(dev));
         select_kernel<real><<<P.Gc, kSelBlock, 0, stream>>>(P);
         CK(cudaGetLastError());
@@ -870,6 +882,154 @@ struct SolverImpl final : SolverBase {
         return B2S_OK;
     }
 
+    // ---- caller-owned tableau (tabular_t of include/tabular.cuh:5-30) ---------------------------
+    int attach(double* table, size_t pitch, int rows, int cols, double* costs, int n_vars) override
+    {
+        if (sizeof(real) != sizeof(double)) return fail(B2S_ERR_ARG, "attach needs an fp64 solver (reference TYPE)");
+        if (world > 1) return fail(B2S_ERR_STATE, "attach is single-GPU only");
+        if (!table || !costs || rows < 2 || cols < 1 || n_vars < 0) return fail(B2S_ERR_ARG, "bad tableau description");
+        if (pitch % 32 != 0 || pitch < (size_t)cols * sizeof(double) || ((size_t)table % 32) != 0)
+            return fail(B2S_ERR_ARG, "tableau pitch/base must be 32-byte aligned (cudaMallocPitch guarantees it)");
+        CK(cudaSetDevice(dev));
+        // scratch sized for this shape; no tableau storage of our own
+        const bool keep_fold = folded;
+        folded = false;
+        world = 1;
+        n = std::max(n_vars, 1);
+        m = cols;
+        m_loc = m;
+        col0 = 0;
+        const long long ld_ = (long long)(pitch / sizeof(double));
+        if ((size_t)rows > cap_rows || (size_t)ld_ > cap_cols || (size_t)n > cap_n) {
+            free_problem();
+            int rc;
+            if ((rc = dmalloc(&T_own, 1))) return rc;
+            if ((rc = dmalloc(&cost_own, 1))) return rc;
+            if ((rc = dmalloc(&rowp, (size_t)rows))) return rc;
+            if ((rc = dmalloc(&col, (size_t)ld_))) return rc;
+            if ((rc = dmalloc(&s, (size_t)ld_))) return rc;
+            if ((rc = dmalloc(&coef, (size_t)ld_))) return rc;
+            if ((rc = dmalloc(&neg, (size_t)ld_))) return rc;
+            if ((rc = dmalloc(&c_dev, (size_t)n))) return rc;
+            if ((rc = dmalloc(&x_dev, (size_t)n))) return rc;
+            if ((rc = dmalloc(&base, (size_t)m))) return rc;
+            if ((rc = dmalloc(&rslot_v, kMaxSlots))) return rc;
+            if ((rc = dmalloc(&rslot_max, kMaxSlots))) return rc;
+            if ((rc = dmalloc(&rslot_i, kMaxSlots))) return rc;
+            if ((rc = dmalloc(&rslot_k, kMaxSlots))) return rc;
+            if ((rc = dmalloc(&cslot_v, kMaxSlots))) return rc;
+            if ((rc = dmalloc(&cslot_i, kMaxSlots))) return rc;
+            if ((rc = dmalloc(&cslot_k, kMaxSlots))) return rc;
+            cap_T = 0;
+            cap_rows = (size_t)rows;
+            cap_cols = (size_t)ld_;
+            cap_n = (size_t)n;
+        }
+        (void)keep_fold;
+        ld = ld_;
+        R1 = Rs = Rc = rows;
+        T = reinterpret_cast<real*>(table);
+        cost = reinterpret_cast<real*>(costs);
+        attached = true;
+        phase = (rows == 1 + n_vars + cols) ? 2 : 1;
+        pivots_p1 = pivots_p2 = 0;
+        sec_load = sec_p1 = sec_p2 = 0;
+        invalidate_graph();
+        fill_params();
+        CK(cudaMemsetAsync(st, 0, sizeof(DevState), stream));
+        state_reset_kernel<<<1, 1, 0, stream>>>(st, 1);
+        CK(cudaGetLastError());
+        stage = kBuilt;
+        return B2S_OK;
+    }
+
+    int set_basis(const int* base_host) override
+    {
+        if (stage == kEmpty || stage == kLoaded || !base_host) return fail(B2S_ERR_STATE, "set_basis needs a built or attached tableau");
+        CK(cudaSetDevice(dev));
+        CK(cudaMemcpyAsync(base, base_host, sizeof(int) * (size_t)m, cudaMemcpyHostToDevice, stream));
+        CK(cudaStreamSynchronize(stream));
+        return B2S_OK;
+    }
+
+    // ---- device-vector primitives of include/reduction.cuh --------------------------------------
+    int run_tournament_device(const real* dvals /* cnt+1 entries, [0] unused */, long long cnt, double* value, unsigned* index)
+    {
+        real* dv = nullptr;
+        int *di = nullptr, *dk = nullptr;
+        DevState* dst = nullptr;
+        CK(cudaMalloc(&dv, sizeof(real) * kMaxSlots));
+        CK(cudaMalloc(&di, sizeof(int) * kMaxSlots));
+        CK(cudaMalloc(&dk, sizeof(int) * kMaxSlots));
+        CK(cudaMalloc(&dst, sizeof(DevState)));
+        CK(cudaMemsetAsync(dst, 0, sizeof(DevState), stream));
+        PivotParams<real> Q{};
+        Q.cost = const_cast<real*>(dvals);
+        Q.Rc = cnt + 1;
+        Q.fold_from = LLONG_MAX;
+        Q.cslot_v = dv;
+        Q.cslot_i = di;
+        Q.cslot_k = dk;
+        Q.st = dst;
+        Q.rule = opt.pivot_rule;
+        Q.Gc = (int)std::max<long long>(1, std::min<long long>((cnt + kSelBlock - 1) / kSelBlock, kMaxSlots));
+        select_kernel<real><<<Q.Gc, kSelBlock, 0, stream>>>(Q);
+        DevState hs;
+        CK(cudaMemcpyAsync(&hs, dst, sizeof(DevState), cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        if (value) *value = hs.cq;
+        if (index) *index = (unsigned)hs.q;
+        cudaFree(dv);
+        cudaFree(di);
+        cudaFree(dk);
+        cudaFree(dst);
+        return B2S_OK;
+    }
+
+    int min_element_device(const double* dvec, long long cnt, double* value, unsigned* index) override
+    {
+        if (sizeof(real) != sizeof(double)) return fail(B2S_ERR_ARG, "fp64 only");
+        if (cnt < 1 || !dvec) return fail(B2S_ERR_ARG, "minElement needs a non-empty device vector");
+        CK(cudaSetDevice(dev));
+        real* tmp = nullptr;  // the reference reduces a scratch copy too (src/reduction.cu:87-89)
+        CK(cudaMalloc(&tmp, sizeof(real) * ((size_t)cnt + 1)));
+        CK(cudaMemcpyAsync(tmp + 1, dvec, sizeof(real) * (size_t)cnt, cudaMemcpyDeviceToDevice, stream));
+        int rc = run_tournament_device(tmp, cnt, value, index);
+        cudaFree(tmp);
+        return rc;
+    }
+
+    int ratio_min_device(const double* known, const double* column, long long cnt, double* value, unsigned* index) override
+    {
+        if (sizeof(real) != sizeof(double)) return fail(B2S_ERR_ARG, "fp64 only");
+        if (cnt < 1 || !known || !column) return fail(B2S_ERR_ARG, "ratio minElement needs two device vectors");
+        CK(cudaSetDevice(dev));
+        real* tmp = nullptr;
+        CK(cudaMalloc(&tmp, sizeof(real) * ((size_t)cnt + 1)));
+        ratio_vector_kernel<real><<<(unsigned)((cnt + 255) / 256), 256, 0, stream>>>(
+            reinterpret_cast<const real*>(known), reinterpret_cast<const real*>(column), cnt, tmp + 1);
+        int rc = run_tournament_device(tmp, cnt, value, index);
+        cudaFree(tmp);
+        return rc;
+    }
+
+    int max_le_zero_device(const double* dvec, long long cnt, int* result) override
+    {
+        if (sizeof(real) != sizeof(double)) return fail(B2S_ERR_ARG, "fp64 only");
+        if (cnt < 1 || !dvec || !result) return fail(B2S_ERR_ARG, "isLessOrEqualThanZero needs a device vector");
+        CK(cudaSetDevice(dev));
+        real* out = nullptr;
+        CK(cudaMalloc(&out, sizeof(real)));
+        max_vector_kernel<real><<<1, kSelBlock, 0, stream>>>(reinterpret_cast<const real*>(dvec), cnt, out);
+        real h = 0;
+        CK(cudaMemcpyAsync(&h, out, sizeof(real), cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        cudaFree(out);
+        const double d = (double)h;  // compare(max) <= 0  <=>  max < 1e-9   (src/reduction.cu:200)
+        *result = (fabs(d) < 1e-9 || d < 0.0) ? 1 : 0;
+        return B2S_OK;
+    }
+
     // ---- kernel-level hooks ------------------------------------------------------------------
     int tournament(const double* vec, long long cnt, double* value, int* index) override
     {
@@ -1130,6 +1290,11 @@ int b2s_bench_update(b2s_solver* s, int launches, int flush_l2, float* ms_each, 
     B2S_FWD(bench_update(launches, flush_l2, ms_each, bytes_per_launch));
 }
 int b2s_dist_init(b2s_solver* s, int rank, int world, const char id[B2S_NCCL_ID_BYTES]) { B2S_FWD(dist_init(rank, world, id)); }
+int b2s_attach_tableau_device(b2s_solver* s, double* table, size_t pitch_bytes, int rows, int cols, double* costs, int n_vars) { B2S_FWD(attach(table, pitch_bytes, rows, cols, costs, n_vars)); }
+int b2s_set_basis(b2s_solver* s, const int* basis_host) { B2S_FWD(set_basis(basis_host)); }
+int b2s_min_element_device(b2s_solver* s, const double* dvec, long long n, double* value, unsigned* index) { B2S_FWD(min_element_device(dvec, n, value, index)); }
+int b2s_ratio_min_device(b2s_solver* s, const double* known_terms, const double* column, long long n, double* value, unsigned* index) { B2S_FWD(ratio_min_device(known_terms, column, n, value, index)); }
+int b2s_max_le_zero_device(b2s_solver* s, const double* dvec, long long n, int* result) { B2S_FWD(max_le_zero_device(dvec, n, result)); }
 int b2s_profile_pivots(b2s_solver* s, int count, float* ms_ratio, float* ms_gather, float* ms_update, long long* pivots_done)
 {
     if (count < 1 || !ms_ratio || !ms_gather || !ms_update) return B2S_ERR_ARG;

@@ -27,4 +27,6 @@ FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -fmad=fa
        -Xcompiler -fPIC,-O2,-ffp-contract=off,-Wall -shared -DB2S_WITH_NCCL -I"$NCCL_INC")
 "$NVCC" "${FLAGS[@]}" ${B2S_PTXAS_V:+-Xptxas -v} -o "$OUT/libb2s.so" "$HERE/b2s_solver.cu" \
     -L"$NCCL_LIB" -l:libnccl.so.2 -Xlinker -rpath,"$NCCL_LIB"
-echo "built $OUT/libb2s.so"
+"$NVCC" -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -fmad=false -Xcompiler -fPIC,-O2,-ffp-contract=off \
+    -shared -o "$OUT/libb2s_compat.so" "$HERE/compat.cu" -L"$OUT" -lb2s -Xlinker -rpath,'$ORIGIN'
+echo "built $OUT/libb2s.so $OUT/libb2s_compat.so"

@@ -1,0 +1,64 @@
+"""Drop-in proof on the GPU box: the reference's own, UNMODIFIED main.cu, compiled against
+include/compat and linked against libb2s_compat.so/libb2s.so (oracle/_ref/SimplexOnCuda_dropin),
+must behave like the stock reference program (oracle/_ref/SimplexOnCuda_ref) on the reference's
+own CLI: same status line, same solution file."""
+import json
+import os
+import subprocess
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(ROOT, "oracle", "_ref", "SimplexOnCuda_ref")
+OURS = os.path.join(ROOT, "oracle", "_ref", "SimplexOnCuda_dropin")
+EXAMPLES = json.load(open(os.path.join(ROOT, "tests", "golden", "examples.json")))
+SOLUTION = "..\\data\\solution.txt"   # literal file name the reference writes on Linux (main.cu:84)
+
+needs = pytest.mark.skipif(not (os.path.exists(REF) and os.path.exists(OURS)),
+                           reason="oracle/_ref binaries not built (needs /root/reference at build time)")
+
+
+def run(exe, cwd, args):
+    os.makedirs(cwd, exist_ok=True)
+    out = subprocess.run([exe] + args, cwd=cwd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout + out.stderr
+    status = [ln for ln in out.stdout.splitlines() if ln.startswith("Problem")]
+    sol = open(os.path.join(cwd, SOLUTION)).read() if os.path.exists(os.path.join(cwd, SOLUTION)) else None
+    return status, sol, out.stdout
+
+
+@needs
+@pytest.mark.parametrize("name,expect", [("smallProblem", "Problem solved!"), ("infeasibleProblem", "Problem INFEASIBLE!"),
+                                         ("unboundedProblem", "Problem UNBOUNDED!")])
+def test_example_files(tmp_path, name, expect):
+    lp = tmp_path / f"{name}.txt"
+    lp.write_text(EXAMPLES[name]["text"])
+    s_ref, sol_ref, _ = run(REF, str(tmp_path / "ref"), ["-f", str(lp)])
+    s_our, sol_our, log = run(OURS, str(tmp_path / "ours"), ["-f", str(lp)])
+    assert s_ref == s_our == [expect]
+    assert sol_ref == sol_our
+    for phase_line in ("Phase 1: Filling Tableau", "Phase 1: Solving auxiliary problem"):
+        assert phase_line in log
+
+
+@needs
+@pytest.mark.parametrize("n,m,seed", [(256, 256, 25856), (512, 256, 51456), (1024, 1024, 103424)])
+def test_seed_files(tmp_path, n, m, seed):
+    """-rf <seedfile>: both programs derive the kernel seeds with this platform's rand()."""
+    sf = tmp_path / "seed.txt"
+    sf.write_text(f"{n} {m} {seed} 1 100")
+    s_ref, sol_ref, _ = run(REF, str(tmp_path / "ref"), ["-rf", str(sf)])
+    s_our, sol_our, _ = run(OURS, str(tmp_path / "ours"), ["-rf", str(sf)])
+    assert s_ref == s_our == ["Problem solved!"]
+    assert sol_ref == sol_our   # n lines "%lf" + "Optimal value: %lf"
+
+
+@needs
+def test_random_flag(tmp_path):
+    """-r vars cons seed (range [-100,100], main.cu:7-8): mostly UNBOUNDED/INFEASIBLE instances."""
+    for seed in (1, 2, 3, 4, 5):
+        s_ref, sol_ref, _ = run(REF, str(tmp_path / f"ref{seed}"), ["-r", "64", "48", str(seed)])
+        s_our, sol_our, _ = run(OURS, str(tmp_path / f"ours{seed}"), ["-r", "64", "48", str(seed)])
+        assert s_ref == s_our and sol_ref == sol_our
