@@ -619,3 +619,42 @@ int main(int argc, char **argv)
     return 0;
 }
 #endif
+
+/* ---- stage-level access to the tournament, for tests of the sharded protocol ---------------
+ * orc_stage1_block: winner of reference stage-1 block `b` when the grid has G blocks
+ * (src/reduction.cu:51-80).  orc_stage2: the second launch (:92-93) over G (value,index) slots. */
+#ifndef ORC_MAIN
+double orc_stage1_block(const double *vec, long N, long G, long b, int *idx)
+{
+    cand_t thr[512];
+    for (int t = 0; t < 512; ++t) {
+        cand_t c = {DBL_MAX, -1};
+        for (long i = b * 512 + t; i < N; i += 512 * G)
+            if (cmp3(vec[i], c.v) < 0) {
+                c.v = vec[i];
+                c.i = (int)i;
+            }
+        thr[t] = c;
+    }
+    cand_t w = block_tree(thr, 512);
+    *idx = w.i;
+    return w.v;
+}
+
+double orc_stage2(const double *slot_v, const int *slot_i, long G, int *idx)
+{
+    cand_t thr[1024];
+    for (int t = 0; t < 1024; ++t) {
+        cand_t c = {DBL_MAX, -1};
+        for (long i = t; i < G; i += 1024)
+            if (cmp3(slot_v[i], c.v) < 0) {
+                c.v = slot_v[i];
+                c.i = slot_i[i];
+            }
+        thr[t] = c;
+    }
+    cand_t w = block_tree(thr, 1024);
+    *idx = w.i;
+    return w.v;
+}
+#endif

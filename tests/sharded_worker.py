@@ -1,0 +1,42 @@
+"""Worker of tests/test_sharded_gpu.py: launched by torchrun, one rank per GPU.  Solves the LPs listed in
+argv sharded over the ranks through the C ABI and prints one JSON line per LP on rank 0."""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch
+import torch.distributed as dist
+
+import simplexoncuda_b200 as S
+from simplexoncuda_b200 import sharding
+
+
+def main():
+    local = int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    cases = json.loads(sys.argv[1])
+    s = S.Solver(device=local)
+    sharding.init_sharded_solver(s, dist)
+    for cs in cases:
+        seeds = S.seed_triplet(cs["seed"], cs["flavour"])
+        s.generate(cs["n"], cs["m"], seeds, cs["lo"], cs["hi"])
+        r = s.solve()
+        out = {"case": cs, "status": r["status"], "pivots": [r["stats"].pivots_phase1, r["stats"].pivots_phase2],
+               "hash": str(r["stats"].trace_hash), "objective": r["objective"], "basis": r["basis"].tolist(),
+               "x_nonzero": int((r["x"] != 0).sum()), "seconds": [r["stats"].seconds_phase1, r["stats"].seconds_phase2]}
+        # every rank must hold the same replicated result
+        box = [None] * dist.get_world_size()
+        dist.all_gather_object(box, (out["status"], out["hash"], out["objective"]))
+        assert all(b == box[0] for b in box), box
+        if dist.get_rank() == 0:
+            print("RESULT " + json.dumps(out), flush=True)
+    s.close()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
