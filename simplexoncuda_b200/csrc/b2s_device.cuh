@@ -29,6 +29,7 @@ constexpr int kRuleBland = 2;
 
 constexpr int kSelBlock = 512;   // reference stage-1 block size (src/reduction.cu:6)
 constexpr int kMaxSlots = 1024;  // reference stage-1 grid cap  (src/reduction.cu:7)
+constexpr int kMaxPeers = 8;     // GPUs of one box
 
 // Device-resident loop state: the host only polls it between batches of pivots.
 struct DevState {
@@ -49,7 +50,7 @@ struct DevState {
     int any_negated;
     unsigned int tile_ticket;  // dynamic tile scheduler of the update kernel
     unsigned int tile_done;
-    int pad;
+    unsigned int ticket_gather;  // P2P sharding: CTAs of the owner's gather kernel that have published
 };
 
 template <typename real>
@@ -240,6 +241,11 @@ struct PivotParams {
     int Gm_loc0;  // first global block owned by this rank
     int Gm_loc;   // blocks owned by this rank
     int Gc;       // cost stage-1 blocks
+    // peer-memory sharding (b2s_p2p.cuh): arena base of every rank as mapped in this process
+    int rank;
+    int world;
+    long long arena_rows;          // capacity of one arena rowp buffer (elements)
+    unsigned char* peers[kMaxPeers];
     // update-kernel tiling
     int log2_tpr;   // log2(threads per tableau row)
     int nchunks;    // column chunks per row

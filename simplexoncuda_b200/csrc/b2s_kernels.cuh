@@ -160,20 +160,21 @@ __global__ void __launch_bounds__(kSelBlock) select_kernel(PivotParams<real> P)
 // When the tableau is sharded the stage-2 part runs in ratio_finish_kernel after the all-gather.
 // ---------------------------------------------------------------------------------------------
 template <typename real>
-__device__ __forceinline__ void ratio_finish(const PivotParams<real>& P, TreeSmem<real>& sm, real* smax)
+__device__ __forceinline__ void ratio_finish(const PivotParams<real>& P, const real* slot_v, const int* slot_i,
+                                             const int* slot_k, const real* slot_max, TreeSmem<real>& sm, real* smax)
 {
     // global max of the entering column
     real mx = Limits<real>::tiny();
-    for (int b = threadIdx.x; b < P.Gm; b += kSelBlock) mx = fmax(mx, __ldcg(P.rslot_max + b));
+    for (int b = threadIdx.x; b < P.Gm; b += kSelBlock) mx = fmax(mx, __ldcg(slot_max + b));
     mx = block_max_512(mx, smax);
     const int tree_rule = (P.rule == kRuleReference) ? kRuleReference : kRuleLowest;
     Cand<real> w;
     if (P.Gm > 1) {
-        stage2_1024(tree_rule, P.rslot_v, P.rslot_i, P.rslot_k, P.Gm, w, sm);
+        stage2_1024(tree_rule, slot_v, slot_i, slot_k, P.Gm, w, sm);
     } else {
-        w.v = __ldcg(P.rslot_v);
-        w.i = __ldcg(P.rslot_i);
-        w.k = __ldcg(P.rslot_k);
+        w.v = __ldcg(slot_v);
+        w.i = __ldcg(slot_i);
+        w.k = __ldcg(slot_k);
     }
     if (threadIdx.x == 0) {
         DevState* st = P.st;
@@ -258,7 +259,7 @@ __global__ void __launch_bounds__(kSelBlock) ratio_kernel(PivotParams<real> P)
     __syncthreads();
     if (!s_flag) return;
     __threadfence();
-    ratio_finish(P, sm, smax);
+    ratio_finish(P, P.rslot_v, P.rslot_i, P.rslot_k, P.rslot_max, sm, smax);
 }
 
 template <typename real>
@@ -270,7 +271,7 @@ __global__ void __launch_bounds__(kSelBlock) ratio_finish_kernel(PivotParams<rea
     const int status = __ldcg(&st->status);
     const long long pivots = __ldcg(&st->pivots), limit = __ldcg(&st->limit);
     if (status != kRunning || pivots >= limit) return;  // ratio_kernel already cleared `live`
-    ratio_finish(P, sm, smax);
+    ratio_finish(P, P.rslot_v, P.rslot_i, P.rslot_k, P.rslot_max, sm, smax);
 }
 
 // ---------------------------------------------------------------------------------------------

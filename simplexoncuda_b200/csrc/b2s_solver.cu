@@ -6,6 +6,7 @@
 #include "../../include/b2s.h"
 #include "b2s_generator.cuh"
 #include "b2s_kernels.cuh"
+#include "b2s_p2p.cuh"
 
 #include <algorithm>
 #include <chrono>
@@ -137,6 +138,11 @@ struct SolverImpl final : SolverBase {
 #ifdef B2S_WITH_NCCL
     ncclComm_t comm = nullptr;
 #endif
+    // peer-memory exchange (b2s_p2p.cuh)
+    bool p2p = false;              // arenas mapped on every rank: the per-pivot exchanges bypass NCCL
+    unsigned char* arena = nullptr;
+    long long arena_rows = 0;
+    unsigned char* peer_ptr[kMaxPeers] = {};
 
     ~SolverImpl() override { release(); }
 
@@ -159,6 +165,7 @@ struct SolverImpl final : SolverBase {
             e = nullptr;
         }
         if (stream) cudaStreamDestroy(stream);
+        close_arena();
 #ifdef B2S_WITH_NCCL
         if (comm) ncclCommDestroy(comm);
         comm = nullptr;
@@ -232,6 +239,61 @@ struct SolverImpl final : SolverBase {
         return B2S_OK;
     }
 
+    void close_arena()
+    {
+        for (int r = 0; r < kMaxPeers; ++r) {
+            if (peer_ptr[r] && peer_ptr[r] != arena) cudaIpcCloseMemHandle(peer_ptr[r]);
+            peer_ptr[r] = nullptr;
+        }
+        cudaFree(arena);
+        arena = nullptr;
+        arena_rows = 0;
+        p2p = false;
+    }
+
+    // Sharded solves: (re)create this rank's arena for `rows` pivot-constraint entries and map every
+    // peer's arena (CUDA IPC handles travel through one ncclAllGather).  Collective over the ranks.
+    int ensure_arena(long long rows)
+    {
+#ifdef B2S_WITH_NCCL
+        if (world <= 1) return B2S_OK;
+        const char* env = getenv("B2S_P2P");
+        if ((env && atoi(env) == 0) || world > kMaxPeers) {
+            close_arena();
+            return B2S_OK;
+        }
+        if (arena && rows <= arena_rows) return B2S_OK;
+        close_arena();
+        const long long cap = (rows + 1023) / 1024 * 1024;
+        CK(cudaMalloc(&arena, arena_bytes<real>(cap)));
+        CK(cudaMemset(arena, 0, arena_bytes<real>(cap)));
+        cudaIpcMemHandle_t mine;
+        CK(cudaIpcGetMemHandle(&mine, arena));
+        unsigned char* hbuf = nullptr;
+        CK(cudaMalloc(&hbuf, sizeof(mine) * (size_t)world));
+        CK(cudaMemcpy(hbuf + sizeof(mine) * (size_t)rank, &mine, sizeof(mine), cudaMemcpyHostToDevice));
+        NK(ncclAllGather(hbuf + sizeof(mine) * (size_t)rank, hbuf, sizeof(mine), ncclChar, comm, stream));
+        CK(cudaStreamSynchronize(stream));
+        std::vector<cudaIpcMemHandle_t> all((size_t)world);
+        CK(cudaMemcpy(all.data(), hbuf, sizeof(mine) * (size_t)world, cudaMemcpyDeviceToHost));
+        cudaFree(hbuf);
+        for (int r = 0; r < world; ++r) {
+            if (r == rank) {
+                peer_ptr[r] = arena;
+            } else {
+                void* ptr = nullptr;
+                CK(cudaIpcOpenMemHandle(&ptr, all[(size_t)r], cudaIpcMemLazyEnablePeerAccess));
+                peer_ptr[r] = (unsigned char*)ptr;
+            }
+        }
+        arena_rows = cap;
+        p2p = true;
+#else
+        (void)rows;
+#endif
+        return B2S_OK;
+    }
+
     // (Re)allocate for an n x m problem and reset the solver state.
     int prepare(int n_, int m_)
     {
@@ -277,6 +339,10 @@ struct SolverImpl final : SolverBase {
         T = T_own;
         cost = cost_own;
         attached = false;
+        {
+            int rc = ensure_arena(R1);
+            if (rc) return rc;
+        }
         CK(cudaMemsetAsync(st, 0, sizeof(DevState), stream));
         pivots_p1 = pivots_p2 = 0;
         sec_load = sec_p1 = sec_p2 = 0;
@@ -375,6 +441,10 @@ struct SolverImpl final : SolverBase {
         P.Gm_loc0 = col0 / kSelBlock;
         P.Gm_loc = world > 1 ? m_loc / kSelBlock : P.Gm;
         P.Gc = (int)std::max<long long>(1, std::min<long long>((Rc - 1 + kSelBlock - 1) / kSelBlock, kMaxSlots));
+        P.rank = rank;
+        P.world = world;
+        P.arena_rows = arena_rows;
+        for (int r = 0; r < kMaxPeers; ++r) P.peers[r] = peer_ptr[r];
         // update-kernel tiling
         const Variant v = variant();
         const int ept = v.vb / (int)sizeof(real);
@@ -534,6 +604,14 @@ struct SolverImpl final : SolverBase {
         negate_kernel<real><<<num_sms * 4, 256, 0, stream>>>(P, neg);
         state_reset_kernel<<<1, 1, 0, stream>>>(st, 1);
         CK(cudaGetLastError());
+#ifdef B2S_WITH_NCCL
+        if (p2p) {
+            // pivot sequence numbers restart at 1: clear this rank's flags, then make sure every rank
+            // has done so before anyone can publish (the all-reduce is the barrier).
+            CK(cudaMemsetAsync(arena, 0, sizeof(ArenaHeader<real>), stream));
+            NK(ncclAllReduce(verdict, verdict, 1, ncclInt, ncclSum, comm, stream));
+        }
+#endif
         stage = kBuilt;
         return B2S_OK;
     }
@@ -576,6 +654,14 @@ struct SolverImpl final : SolverBase {
 
     int enqueue_pivot()
     {
+        if (world > 1 && p2p) {
+            // exchanges done by the kernels themselves over NVLink peer memory (b2s_p2p.cuh)
+            ratio_p2p_kernel<real><<<P.Gm_loc, kSelBlock, 0, stream>>>(P);
+            gather_p2p_kernel<real><<<(unsigned)((Rs + 255) / 256), 256, 0, stream>>>(P);
+            svec_p2p_kernel<real><<<(unsigned)((std::max(Rs, ld) + 255) / 256), 256, 0, stream>>>(P);
+            update_fn()<<<upd_grid, kSelBlock, 0, stream>>>(P);
+            return B2S_OK;
+        }
 #ifdef B2S_WITH_NCCL
         if (world > 1) return enqueue_pivot_sharded();
 #endif
@@ -623,7 +709,7 @@ struct SolverImpl final : SolverBase {
 
     int launch_batch(int batch)
     {
-        const bool graphable = opt.use_graph && world == 1;
+        const bool graphable = opt.use_graph && (world == 1 || p2p);
         if (!graphable) {
             for (int k = 0; k < batch; ++k) {
                 int rc = enqueue_pivot();
@@ -673,7 +759,7 @@ struct SolverImpl final : SolverBase {
         // looks at the state; a batch enqueued after the phase ended (or the budget ran out) costs only
         // its early-exit launches because every kernel checks the device-resident status/limit first.
         const int full = pick_batch();
-        const bool graphable = opt.use_graph && world == 1;
+        const bool graphable = opt.use_graph && (world == 1 || p2p);
         long long enq = 0;  // pivots enqueued so far (upper bound on pivots made)
         auto enqueue = [&](int slot) -> int {
             long long left = limit - start - enq;
@@ -1149,6 +1235,7 @@ struct SolverImpl final : SolverBase {
             ncclCommDestroy(comm);
             comm = nullptr;
         }
+        close_arena();
         rank = rank_;
         world = world_;
         if (world > 1) {
