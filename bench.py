@@ -56,6 +56,7 @@ def parse():
     ap.add_argument("--cpu-pivots", type=int, default=0, help="pivot budget of the cpu_baseline sample (0 = auto)")
     ap.add_argument("--skip-zero-rows", action="store_true")
     ap.add_argument("--update-variant", type=int, default=8)
+    ap.add_argument("--no-persistent", action="store_true", help="three launches per pivot instead of the loop kernel")
     return ap.parse_args()
 
 
@@ -223,7 +224,8 @@ def run_b2s(a):
 
     n, m, P = a.vars, a.constraints, a.pivots_per_step
     seeds = S.seed_triplet(default_seed(a), S.RAND_MSVC)
-    s = S.Solver(device=local, skip_zero_rows=a.skip_zero_rows, update_variant=a.update_variant)
+    s = S.Solver(device=local, skip_zero_rows=a.skip_zero_rows, update_variant=a.update_variant,
+                 persistent=not a.no_persistent)
     if world > 1:
         uid = [S.dist_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
@@ -267,7 +269,7 @@ def run_b2s(a):
         achieved = bytes_per_pivot / (upd * 1e-3) / 1e9
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "update_kernel_traffic.json")
-        if os.path.exists(tpath):
+        if os.path.exists(tpath) and (n, m) == (8192, 8192):   # the ncu capture under profiles/ is of this workload
             traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
         roofline = {"bound": "hbm", "kernel": "update_kernel (fused rank-1 update + cost update + entering tournament)",
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
@@ -287,10 +289,14 @@ def run_b2s(a):
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(a), "pivots_per_step": P, "phase": 1,
                        "tableau_rows_stored": dims["rows_stored"], "tableau_bytes": dims["rows_stored"] * m * elem,
-                       "l2": "inputs larger than L2 (tableau 1.07 GB vs 126 MB), no flush needed",
+                       "l2": (f"inputs larger than L2 (tableau {dims['rows_stored'] * m * elem / 1e9:.2f} GB vs 126 MB), no flush"
+                              if dims["rows_stored"] * m * elem > 4 * 126e6 else
+                              f"tableau {dims['rows_stored'] * m * elem / 1e6:.1f} MB is L2-resident: latency-bound regime, no flush"),
                        "parallelism": f"constraint slabs x{world}" if world > 1 else "single GPU",
-                       "skip_zero_rows": bool(a.skip_zero_rows), "update_variant": a.update_variant},
-            "clocks": clocks, "gpu_launches": 3 * pivots * (1 if world == 1 else 2), "wall_s_timed_region": wall}
+                       "skip_zero_rows": bool(a.skip_zero_rows), "update_variant": a.update_variant,
+                       "loop": "3 launches per pivot (CUDA graph)" if a.no_persistent else
+                               "persistent cooperative loop kernel (1 launch per batch of pivots)"},
+            "clocks": clocks, "gpu_launches": (3 * pivots * (1 if world == 1 else 2)) if a.no_persistent else pivots, "wall_s_timed_region": wall}
     if rows_note is not None:
         line["config"]["rows_streamed_fraction"] = rows_note
     if roofline:
@@ -303,7 +309,8 @@ def run_b2s(a):
             A, b, c = g.copy_problem()
         Ap = torch.from_numpy(A).pin_memory(); bp = torch.from_numpy(b).pin_memory(); cp = torch.from_numpy(c).pin_memory()
         del A
-        with S.Solver(device=local, skip_zero_rows=a.skip_zero_rows, update_variant=a.update_variant) as e:
+        with S.Solver(device=local, skip_zero_rows=a.skip_zero_rows, update_variant=a.update_variant,
+                      persistent=not a.no_persistent) as e:
             torch.cuda.synchronize()
             t0 = time.time()
             e.load(Ap.numpy(), bp.numpy(), cp.numpy())

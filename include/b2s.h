@@ -66,7 +66,9 @@ typedef struct b2s_options {
     long long trace_capacity; /* (q,p) pairs kept on the device for b2s_copy_trace; 0 = default 1<<20 */
     int update_variant;   /* rank-1 update kernel variant (default 8: 256-bit accesses, 8 rows in flight,
                              device-wide ticket scheduler over 8-row tiles); others exist for tuning  */
-    int reserved[7];
+    int persistent;       /* 1 (default): run each batch of pivots as ONE persistent cooperative kernel with
+                             device-wide barriers between the phases; 0: three launches per pivot       */
+    int reserved[6];
 } b2s_options;
 
 typedef struct b2s_stats {

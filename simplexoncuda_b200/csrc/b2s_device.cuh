@@ -51,6 +51,8 @@ struct DevState {
     unsigned int tile_ticket;  // dynamic tile scheduler of the update kernel
     unsigned int tile_done;
     unsigned int ticket_gather;  // P2P sharding: CTAs of the owner's gather kernel that have published
+    unsigned int bar_count;      // grid barrier of the persistent loop kernel (zeroed by the host per launch)
+    unsigned int pad2[3];
 };
 
 template <typename real>

@@ -27,6 +27,8 @@ __device__ __forceinline__ Pack<16> ld_pack(const Pack<16>* p)
         asm volatile("ld.global.v2.b64 {%0,%1}, [%2];" : "=l"(r.w[0]), "=l"(r.w[1]) : "l"(p));
     else if (HINT == 1)
         asm volatile("ld.global.cs.v2.b64 {%0,%1}, [%2];" : "=l"(r.w[0]), "=l"(r.w[1]) : "l"(p));
+    else if (HINT == 3)
+        asm volatile("ld.global.cg.v2.b64 {%0,%1}, [%2];" : "=l"(r.w[0]), "=l"(r.w[1]) : "l"(p));
     else
         asm volatile("ld.global.L1::no_allocate.v2.b64 {%0,%1}, [%2];" : "=l"(r.w[0]), "=l"(r.w[1]) : "l"(p));
     return r;
@@ -49,6 +51,10 @@ __device__ __forceinline__ Pack<32> ld_pack(const Pack<32>* p)
                      : "l"(p));
     else if (HINT == 1)
         asm volatile("ld.global.cs.v4.b64 {%0,%1,%2,%3}, [%4];"
+                     : "=l"(r.w[0]), "=l"(r.w[1]), "=l"(r.w[2]), "=l"(r.w[3])
+                     : "l"(p));
+    else if (HINT == 3)
+        asm volatile("ld.global.cg.v4.b64 {%0,%1,%2,%3}, [%4];"
                      : "=l"(r.w[0]), "=l"(r.w[1]), "=l"(r.w[2]), "=l"(r.w[3])
                      : "l"(p));
     else
@@ -84,13 +90,21 @@ union PackView {
 // pivot of a phase.  Block b plays reference stage-1 block b; the CTA that draws the last ticket
 // plays the stage-2 block and publishes (cq, q) and the optimality verdict (src/solver.cu:87-88).
 // ---------------------------------------------------------------------------------------------
-template <typename real, bool kUpdate>
-__device__ __forceinline__ void cost_select_blocks(const PivotParams<real>& P, TreeSmem<real>& sm, int* s_flag)
+// Read-only vectors are fetched through the non-coherent path in the per-pivot kernels (they were
+// written by an earlier launch); inside the persistent loop kernel they change between grid barriers
+// and must come from L2 (COH).
+template <bool COH, typename X>
+__device__ __forceinline__ X ld_vec(const X* p)
+{
+    return COH ? __ldcg(p) : __ldg(p);
+}
+
+template <typename real, bool kUpdate, bool COH = false>
+__device__ __forceinline__ void cost_select_blocks(const PivotParams<real>& P, const real* rowp, real sc,
+                                                   TreeSmem<real>& sm, int* s_flag)
 {
     const long long Nc = P.Rc - 1;
     const int rule = P.rule;
-    real sc = 0;
-    if (kUpdate) sc = (real)__ldcg(&P.st->sc);
     for (int b = blockIdx.x; b < P.Gc; b += gridDim.x) {
         Cand<real> c;
         c.v = Limits<real>::big();
@@ -98,9 +112,9 @@ __device__ __forceinline__ void cost_select_blocks(const PivotParams<real>& P, T
         c.k = -1;
         for (long long i = (long long)b * kSelBlock + threadIdx.x; i < Nc; i += (long long)kSelBlock * P.Gc) {
             const long long j = 1 + i;
-            real v = P.cost[j];
+            real v = COH ? __ldcg(P.cost + j) : P.cost[j];
             if (kUpdate) {
-                v = fma_r(sc, __ldg(P.rowp + stored_row(P, j)), v);  // src/solver.cu:54
+                v = fma_r(sc, ld_vec<COH>(rowp + stored_row(P, j)), v);  // src/solver.cu:54
                 P.cost[j] = v;
             }
             Cand<real> o;
@@ -109,7 +123,8 @@ __device__ __forceinline__ void cost_select_blocks(const PivotParams<real>& P, T
             o.k = (rule == kRuleBland) ? (cmp3((double)v, 0.0) < 0 ? (int)i : -1) : (int)i;
             if (beats(rule, o, c)) c = o;
         }
-        if (kUpdate && b == 0 && threadIdx.x == 0) P.cost[0] = fma_r(sc, __ldg(P.rowp), P.cost[0]);  // objective
+        if (kUpdate && b == 0 && threadIdx.x == 0)
+            P.cost[0] = fma_r(sc, ld_vec<COH>(rowp), COH ? __ldcg(P.cost) : P.cost[0]);  // objective
         block_tree_512(rule, c, sm);
         if (threadIdx.x == 0) {
             P.cslot_v[b] = c.v;
@@ -147,7 +162,7 @@ __global__ void __launch_bounds__(kSelBlock) select_kernel(PivotParams<real> P)
 {
     __shared__ TreeSmem<real> sm;
     __shared__ int s_flag;
-    cost_select_blocks<real, false>(P, sm, &s_flag);
+    cost_select_blocks<real, false>(P, P.rowp, (real)0, sm, &s_flag);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -350,23 +365,16 @@ __global__ void __launch_bounds__(256) svec_kernel(PivotParams<real> P)
 }
 
 // ---------------------------------------------------------------------------------------------
-// update_kernel: the HBM-bound kernel.  T[r][i] = fma(s[i], rowp[r], T[r][i]) over the whole
-// stored tableau, read once and written once (2*Rs*ld*sizeof(real) bytes), persistent CTAs of
-// 512 threads.  Each thread owns VB bytes of consecutive columns (its s values stay in
-// registers) and walks rows in unrolled groups of U independent 128/256-bit loads.  The first Gc
-// CTAs first update the cost vector and run the next pivot's entering-column tournament.
+// stream_tiles: the tile loop of the rank-1 update, shared by update_kernel (one launch per pivot)
+// and pivot_loop_kernel (persistent).  `svec` holds s = -a_q/pivot; when it is null the thread
+// derives its s values from the entering-column snapshot (`colv`), the pivot and the pivot column
+// index lp -- the same division, so the same bits.
 // ---------------------------------------------------------------------------------------------
-template <typename real, int VB, int U, int HINT, bool SKIP, bool DYN>
-__global__ void __launch_bounds__(kSelBlock, (VB * U <= 128) ? 2 : 1) update_kernel(PivotParams<real> P)
+template <typename real, int VB, int U, int HINT, bool SKIP, bool DYN, bool COH>
+__device__ __forceinline__ void stream_tiles(const PivotParams<real>& P, const real* rowp, const real* svec,
+                                             const real* colv, real piv, long long lp, long long* s_next)
 {
     constexpr int EPT = VB / (int)sizeof(real);
-    __shared__ TreeSmem<real> sm;
-    __shared__ int s_flag;
-    __shared__ long long s_next;
-    if (!__ldcg(&P.st->live)) return;
-
-    if (blockIdx.x < P.Gc) cost_select_blocks<real, true>(P, sm, &s_flag);
-
     const int tx = threadIdx.x & ((1 << P.log2_tpr) - 1);
     const int ty = threadIdx.x >> P.log2_tpr;
     const int rpp = kSelBlock >> P.log2_tpr;           // rows per pass
@@ -380,7 +388,7 @@ __global__ void __launch_bounds__(kSelBlock, (VB * U <= 128) ? 2 : 1) update_ker
     long long tile = blockIdx.x;
     while (tile < P.ntiles) {
         if (DYN && threadIdx.x == 0)
-            s_next = (long long)atomicAdd(&P.st->tile_ticket, 1u) + gridDim.x;
+            *s_next = (long long)atomicAdd(&P.st->tile_ticket, 1u) + gridDim.x;
         const int chunk = (int)(tile % P.nchunks);
         const long long rb = tile / P.nchunks;
         const long long c = chunk * chunk_cols + (long long)tx * EPT;
@@ -388,7 +396,14 @@ __global__ void __launch_bounds__(kSelBlock, (VB * U <= 128) ? 2 : 1) update_ker
             if (chunk != cur_chunk) {
                 cur_chunk = chunk;
 #pragma unroll
-                for (int e = 0; e < EPT; ++e) sreg[e] = __ldg(P.s + c + e);
+                for (int e = 0; e < EPT; ++e) {
+                    if (svec) {
+                        sreg[e] = ld_vec<COH>(svec + c + e);
+                    } else {
+                        const long long ci = c + e;
+                        sreg[e] = (ci < P.m_loc && ci != lp) ? div_r(-ld_vec<COH>(colv + ci), piv) : (real)0;
+                    }
+                }
             }
             const long long r0 = rb * tile_rows + ty;
             for (int g = 0; g < P.tile_groups; ++g) {
@@ -398,7 +413,7 @@ __global__ void __launch_bounds__(kSelBlock, (VB * U <= 128) ? 2 : 1) update_ker
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     const long long r = r0 + (long long)(g * U + u) * rpp;
-                    a[u] = (r < P.Rs) ? __ldg(P.rowp + r) : (real)0;
+                    a[u] = (r < P.Rs) ? ld_vec<COH>(rowp + r) : (real)0;
                     ptr[u] = reinterpret_cast<Pack<VB>*>(P.T + r * P.ld + c);
                     if (!SKIP && !(r < P.Rs)) ptr[u] = nullptr;
                     if (SKIP && a[u] == (real)0) ptr[u] = nullptr;
@@ -417,12 +432,33 @@ __global__ void __launch_bounds__(kSelBlock, (VB * U <= 128) ? 2 : 1) update_ker
         }
         if (DYN) {
             __syncthreads();
-            tile = s_next;
+            tile = *s_next;
             __syncthreads();
         } else {
             tile += gridDim.x;
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// update_kernel: the HBM-bound kernel.  T[r][i] = fma(s[i], rowp[r], T[r][i]) over the whole
+// stored tableau, read once and written once (2*Rs*ld*sizeof(real) bytes), persistent CTAs of
+// 512 threads.  Each thread owns VB bytes of consecutive columns (its s values stay in
+// registers) and walks rows in unrolled groups of U independent 128/256-bit loads.  The first Gc
+// CTAs first update the cost vector and run the next pivot's entering-column tournament.
+// ---------------------------------------------------------------------------------------------
+template <typename real, int VB, int U, int HINT, bool SKIP, bool DYN>
+__global__ void __launch_bounds__(kSelBlock, (VB * U <= 128) ? 2 : 1) update_kernel(PivotParams<real> P)
+{
+    constexpr int EPT = VB / (int)sizeof(real);
+    __shared__ TreeSmem<real> sm;
+    __shared__ int s_flag;
+    __shared__ long long s_next;
+    if (!__ldcg(&P.st->live)) return;
+
+    if (blockIdx.x < P.Gc) cost_select_blocks<real, true>(P, P.rowp, (real)__ldcg(&P.st->sc), sm, &s_flag);
+
+    stream_tiles<real, VB, U, HINT, SKIP, DYN, false>(P, P.rowp, P.s, nullptr, (real)0, -1, &s_next);
     if (DYN) {
         // the last CTA to leave re-arms the ticket counters for the next launch
         if (threadIdx.x == 0) {

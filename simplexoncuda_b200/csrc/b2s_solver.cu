@@ -7,6 +7,7 @@
 #include "b2s_generator.cuh"
 #include "b2s_kernels.cuh"
 #include "b2s_p2p.cuh"
+#include "b2s_persistent.cuh"
 
 #include <algorithm>
 #include <chrono>
@@ -128,6 +129,7 @@ struct SolverImpl final : SolverBase {
 
     PivotParams<real> P{};
     int upd_grid = 0;
+    int loop_grid = 0;  // persistent loop kernel: co-resident CTAs
     cudaGraphExec_t graph_exec = nullptr;
     int graph_batch = 0;
     long long pivots_p1 = 0, pivots_p2 = 0;
@@ -377,7 +379,14 @@ struct SolverImpl final : SolverBase {
                                                     {16, 4, 0, 1}, {32, 8, 1, 1}, {32, 8, 2, 1}, {16, 8, 0, 1}};
         int v = opt.update_variant;
         if (v < 0 || v >= kNumVariants) v = 8;
+        if (use_persistent()) v = 8;  // the loop kernel is built for the 256-bit / 8-row / ticketed geometry
         return table[v];
+    }
+    bool use_persistent() const { return opt.persistent != 0 && (world == 1 || p2p); }
+    typedef void (*LoopFn)(PivotParams<real>, int);
+    LoopFn loop_fn() const
+    {
+        return opt.skip_zero_rows ? (LoopFn)pivot_loop_kernel<real, 32, 8, true> : (LoopFn)pivot_loop_kernel<real, 32, 8, false>;
     }
     typedef void (*UpdateFn)(PivotParams<real>);
     template <int VB, int U, int HINT, bool DYN>
@@ -472,6 +481,11 @@ struct SolverImpl final : SolverBase {
         P.ntiles = ((Rs + rows_tile - 1) / rows_tile) * P.nchunks;
         upd_grid = (int)std::max<long long>(std::min<long long>(grid, P.ntiles), std::min(P.Gc, grid));
         upd_grid = std::max(upd_grid, 1);
+        if (opt.persistent) {
+            int occ_l = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_l, loop_fn(), kSelBlock, 0);
+            loop_grid = num_sms * std::max(1, std::min(occ_l, 1));
+        }
     }
 
     // ---- problem input -------------------------------------------------------------------------
@@ -709,6 +723,15 @@ struct SolverImpl final : SolverBase {
 
     int launch_batch(int batch)
     {
+        if (use_persistent()) {
+            // one cooperative launch runs the whole batch of pivots (b2s_persistent.cuh)
+            CK(cudaMemsetAsync(&st->bar_count, 0, sizeof(unsigned), stream));
+            PivotParams<real> Pk = P;
+            int bk = batch;
+            void* args[] = {&Pk, &bk};
+            CK(cudaLaunchCooperativeKernel((const void*)loop_fn(), dim3((unsigned)loop_grid), dim3(kSelBlock), args, 0, stream));
+            return B2S_OK;
+        }
         const bool graphable = opt.use_graph && (world == 1 || p2p);
         if (!graphable) {
             for (int k = 0; k < batch; ++k) {
@@ -1282,6 +1305,7 @@ void b2s_default_options(b2s_options* opt)
     opt->max_pivots = 0;
     opt->trace_capacity = 0;
     opt->update_variant = 8;
+    opt->persistent = 1;
 }
 
 int b2s_device_count(void)

@@ -58,13 +58,14 @@ def test_generator_matches_oracle(S, n, m, lo, hi):
 
 
 # ---- stepping parity: every intermediate state -----------------------------------------------------
+@pytest.mark.parametrize("persistent", [True, False])
 @pytest.mark.parametrize("fold", [True, False])
 @pytest.mark.parametrize("n,m,lo,hi,seed", [(24, 16, -100, 100, 3), (64, 64, 1, 100, 5), (100, 130, -100, 100, 9),
                                             (600, 520, 1, 100, 11)])
-def test_stepping_bit_exact(S, fold, n, m, lo, hi, seed):
+def test_stepping_bit_exact(S, persistent, fold, n, m, lo, hi, seed):
     A, b, c = O.generate(n, m, O.seed_triplet(seed, 0), lo, hi)
     o = O.Oracle(A, b, c)
-    with S.Solver(fold_artificials=fold, use_graph=False) as s:
+    with S.Solver(fold_artificials=fold, use_graph=False, persistent=persistent) as s:
         s.load(A, b, c)
         s.build_phase1(); o.build_phase1()
         assert same(s.tableau(), o.tableau()) and same(s.costs(), o.costs()) and same(s.basis(), o.basis())
@@ -144,12 +145,13 @@ def test_mixed_sign_suite(S, n, m):
         check_solve(S, A, b, c, max_pivots=200000)
 
 
+@pytest.mark.parametrize("persistent", [True, False])
 @pytest.mark.parametrize("rule", [1, 2])
-def test_alternative_pivot_rules(S, rule):
+def test_alternative_pivot_rules(S, rule, persistent):
     for n, m, lo in ((64, 64, 1), (48, 32, -100), (32, 48, -100), (300, 200, 1)):
         for seed in (1, 2, 3):
             A, b, c = O.generate(n, m, O.seed_triplet(seed, 1), lo, 100)
-            check_solve(S, A, b, c, rule=rule, max_pivots=500000)
+            check_solve(S, A, b, c, rule=rule, max_pivots=500000, persistent=persistent)
 
 
 def test_blands_rule_breaks_cycling(S):
@@ -165,7 +167,9 @@ def test_blands_rule_breaks_cycling(S):
 @pytest.mark.parametrize("opts", [dict(fold_artificials=False), dict(skip_zero_rows=True), dict(use_graph=False),
                                   dict(update_variant=2), dict(update_variant=4), dict(update_variant=1),
                                   dict(batch=1), dict(update_variant=7, skip_zero_rows=True), dict(update_variant=4),
-                                  dict(update_variant=10), dict(update_variant=9, skip_zero_rows=True), dict(update_variant=0)])
+                                  dict(update_variant=10), dict(update_variant=9, skip_zero_rows=True), dict(update_variant=0),
+                                  dict(persistent=False), dict(persistent=False, use_graph=False),
+                                  dict(persistent=False, skip_zero_rows=True), dict(persistent=True, batch=3)])
 def test_options_do_not_change_results(S, opts):
     A, b, c = O.generate(300, 260, O.seed_triplet(77, 1), 1, 100)
     check_solve(S, A, b, c, **opts)
@@ -225,3 +229,34 @@ def test_full_size_properties(S):
         assert np.all(np.abs(costs[1 + basis]) < 1e-6)
         for i in np.flatnonzero(basis != (n + m + np.arange(m)))[:5]:
             assert basis[i] == qp[qp[:, 1] == i][-1, 0]
+
+
+# ---- fp32 mode (no reference counterpart: the reference does not compile with TYPE=float) ----------
+@pytest.mark.parametrize("n,m,seed", [(64, 64, 3), (256, 256, 25856), (512, 256, 51456), (300, 700, 9)])
+def test_fp32_objective_close_to_fp64_oracle(S, n, m, seed):
+    """fp32 parity is unpinned against the reference; the bar is the north star's: same status and an
+    objective within 1e-4 relative of the fp64 oracle (the pivot path may legitimately differ)."""
+    A, b, c = O.generate(n, m, O.seed_triplet(seed, 1), 1, 100)
+    ref = O.Oracle(A, b, c).two_phase()
+    with S.Solver(dtype=S.F32, max_pivots=200000) as s:
+        s.load(A, b, c)
+        r = s.solve()
+    assert r["status"] == ref["status"] == 0
+    assert abs(r["objective"] - ref["objective"]) <= 1e-4 * abs(ref["objective"])
+    # the fp32 solution must be (nearly) feasible for the fp64 problem
+    assert np.all(A.T @ r["x"] <= b * (1 + 1e-3) + 1e-3) and np.all(r["x"] >= 0)
+
+
+def test_fp32_generator_and_examples(S):
+    with S.Solver(dtype=S.F32) as s:
+        s.generate(100, 64, (1, 2, 3), 1, 100)
+        A32, b32, c32 = s.copy_problem()
+    A, b, c = O.generate(100, 64, (1, 2, 3), 1, 100)
+    assert np.array_equal(A32, A.astype(np.float32).astype(np.float64))
+    assert np.array_equal(b32, b.astype(np.float32).astype(np.float64))
+    for name in ("smallProblem", "infeasibleProblem", "unboundedProblem"):
+        p = S.readProblemFromFile(io.StringIO(EXAMPLES[name]["text"]))
+        st, x, obj = S.twoPhaseMethod(p, dtype=S.F32)
+        assert st == EXAMPLES[name]["status"]
+        if st == 0:
+            assert abs(obj - EXAMPLES[name]["objective"]) <= 1e-4 * EXAMPLES[name]["objective"]
