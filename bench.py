@@ -56,7 +56,8 @@ def parse():
     ap.add_argument("--cpu-pivots", type=int, default=0, help="pivot budget of the cpu_baseline sample (0 = auto)")
     ap.add_argument("--skip-zero-rows", action="store_true")
     ap.add_argument("--update-variant", type=int, default=8)
-    ap.add_argument("--no-persistent", action="store_true", help="three launches per pivot instead of the loop kernel")
+    ap.add_argument("--loop", default="auto", choices=["auto", "persistent", "launches"],
+                    help="persistent cooperative loop kernel, three launches per pivot (CUDA graph), or the library's choice")
     return ap.parse_args()
 
 
@@ -225,7 +226,7 @@ def run_b2s(a):
     n, m, P = a.vars, a.constraints, a.pivots_per_step
     seeds = S.seed_triplet(default_seed(a), S.RAND_MSVC)
     s = S.Solver(device=local, skip_zero_rows=a.skip_zero_rows, update_variant=a.update_variant,
-                 persistent=not a.no_persistent)
+                 persistent={"auto": "auto", "persistent": True, "launches": False}[a.loop])
     if world > 1:
         uid = [S.dist_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
@@ -234,6 +235,10 @@ def run_b2s(a):
     s.build_phase1(); s.price_out(); s.select_entering()
     dims = s.dims()
     elem = 8
+    slab_bytes = dims["rows_stored"] * (m // world) * elem
+    persistent_on = a.loop == "persistent" or (a.loop == "auto" and (world > 1 or slab_bytes < 192e6))
+    loop_mode = ("persistent cooperative loop kernel (1 launch per batch of pivots)" if persistent_on
+                 else "3 launches per pivot replayed as a CUDA graph")
     bytes_per_pivot = 2.0 * dims["rows_stored"] * (m // world) * elem  # per rank: read + write of the stored slab
 
     for _ in range(a.warmup):
@@ -294,9 +299,8 @@ def run_b2s(a):
                               f"tableau {dims['rows_stored'] * m * elem / 1e6:.1f} MB is L2-resident: latency-bound regime, no flush"),
                        "parallelism": f"constraint slabs x{world}" if world > 1 else "single GPU",
                        "skip_zero_rows": bool(a.skip_zero_rows), "update_variant": a.update_variant,
-                       "loop": "3 launches per pivot (CUDA graph)" if a.no_persistent else
-                               "persistent cooperative loop kernel (1 launch per batch of pivots)"},
-            "clocks": clocks, "gpu_launches": (3 * pivots * (1 if world == 1 else 2)) if a.no_persistent else pivots, "wall_s_timed_region": wall}
+                       "loop": loop_mode},
+            "clocks": clocks, "gpu_launches": pivots if "persistent" in loop_mode else 3 * pivots + (pivots if world > 1 else 0), "wall_s_timed_region": wall}
     if rows_note is not None:
         line["config"]["rows_streamed_fraction"] = rows_note
     if roofline:
@@ -310,7 +314,7 @@ def run_b2s(a):
         Ap = torch.from_numpy(A).pin_memory(); bp = torch.from_numpy(b).pin_memory(); cp = torch.from_numpy(c).pin_memory()
         del A
         with S.Solver(device=local, skip_zero_rows=a.skip_zero_rows, update_variant=a.update_variant,
-                      persistent=not a.no_persistent) as e:
+                      persistent={"auto": "auto", "persistent": True, "launches": False}[a.loop]) as e:
             torch.cuda.synchronize()
             t0 = time.time()
             e.load(Ap.numpy(), bp.numpy(), cp.numpy())

@@ -66,8 +66,9 @@ typedef struct b2s_options {
     long long trace_capacity; /* (q,p) pairs kept on the device for b2s_copy_trace; 0 = default 1<<20 */
     int update_variant;   /* rank-1 update kernel variant (default 8: 256-bit accesses, 8 rows in flight,
                              device-wide ticket scheduler over 8-row tiles); others exist for tuning  */
-    int persistent;       /* 1 (default): run each batch of pivots as ONE persistent cooperative kernel with
-                             device-wide barriers between the phases; 0: three launches per pivot       */
+    int persistent;       /* 1: run each batch of pivots as ONE persistent cooperative kernel with device-wide
+                             barriers between the phases; 0: three launches per pivot (CUDA graph);
+                             2 (default): the loop kernel for L2-sized or sharded tableaux, launches otherwise */
     int reserved[6];
 } b2s_options;
 

@@ -393,18 +393,6 @@ __device__ __forceinline__ void stream_tiles(const PivotParams<real>& P, const r
         const long long rb = tile / P.nchunks;
         const long long c = chunk * chunk_cols + (long long)tx * EPT;
         if (c < P.ld) {
-            if (chunk != cur_chunk) {
-                cur_chunk = chunk;
-#pragma unroll
-                for (int e = 0; e < EPT; ++e) {
-                    if (svec) {
-                        sreg[e] = ld_vec<COH>(svec + c + e);
-                    } else {
-                        const long long ci = c + e;
-                        sreg[e] = (ci < P.m_loc && ci != lp) ? div_r(-ld_vec<COH>(colv + ci), piv) : (real)0;
-                    }
-                }
-            }
             const long long r0 = rb * tile_rows + ty;
             for (int g = 0; g < P.tile_groups; ++g) {
                 real a[U];
@@ -421,6 +409,19 @@ __device__ __forceinline__ void stream_tiles(const PivotParams<real>& P, const r
 #pragma unroll
                 for (int u = 0; u < U; ++u)
                     if (ptr[u]) v[u].p = ld_pack<HINT>(ptr[u]);
+                // the thread's s values are (re)computed while the tile's loads are in flight
+                if (chunk != cur_chunk) {
+                    cur_chunk = chunk;
+#pragma unroll
+                    for (int e = 0; e < EPT; ++e) {
+                        if (svec) {
+                            sreg[e] = ld_vec<COH>(svec + c + e);
+                        } else {
+                            const long long ci = c + e;
+                            sreg[e] = (ci < P.m_loc && ci != lp) ? div_r(-ld_vec<COH>(colv + ci), piv) : (real)0;
+                        }
+                    }
+                }
 #pragma unroll
                 for (int u = 0; u < U; ++u)
                     if (ptr[u]) {

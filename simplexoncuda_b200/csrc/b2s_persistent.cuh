@@ -57,8 +57,16 @@ __device__ __forceinline__ bool grid_barrier(unsigned* counter, unsigned& epoch,
     return *s_ok != 0;
 }
 
+// Phase D's streaming loop is kept out of line so that it gets the same register allocation as the
+// stand-alone update_kernel (8 x 256-bit loads in flight need 64 data registers of the 128 available).
 template <typename real, int VB, int U, bool SKIP>
-__global__ void __launch_bounds__(kSelBlock, 1) pivot_loop_kernel(PivotParams<real> P, int batch)
+__device__ __noinline__ void stream_phase(const PivotParams<real>& P, const real* rowp, long long* s_next)
+{
+    stream_tiles<real, VB, U, 3, SKIP, true, true>(P, rowp, P.s, nullptr, (real)0, -1, s_next);
+}
+
+template <typename real, int VB, int U, bool SKIP>
+__global__ void __launch_bounds__(kSelBlock, 1) pivot_loop_kernel(const __grid_constant__ PivotParams<real> P, int batch)
 {
     __shared__ TreeSmem<real> sm;
     __shared__ real smax[32];
@@ -205,12 +213,12 @@ __global__ void __launch_bounds__(kSelBlock, 1) pivot_loop_kernel(PivotParams<re
             st->tile_ticket = 0;  // every CTA left phase D of the previous pivot before the last barrier
         }
 
-        // ---- phase C: gather the raw pivot constraint, normalise the pivot column in place ---------
+        // ---- phase C: gather the raw pivot constraint, normalise the pivot column in place, build s ----
         const long long lp = (long long)p - P.col0;
         const bool owner = lp >= 0 && lp < P.m_loc;
         real piv = 0;
-        if (owner) piv = __ldcg(P.col + lp);
         if (owner) {
+            piv = __ldcg(P.col + lp);
             long long nz = 0;
             for (long long r = gtid; r < P.Rs; r += gstride) {
                 real* e = P.T + r * P.ld + lp;
@@ -225,6 +233,10 @@ __global__ void __launch_bounds__(kSelBlock, 1) pivot_loop_kernel(PivotParams<re
             }
             if (sharded) __threadfence_system();
             if (P.skip_zero && nz) atomicAdd((unsigned long long*)&st->rows_streamed, (unsigned long long)nz);
+        }
+        if (!sharded) {  // one GPU: the pivot is local, s can be built before the barrier
+            for (long long i = gtid; i < P.ld; i += gstride)
+                P.s[i] = (i < P.m_loc && i != lp) ? div_r(-__ldcg(P.col + i), piv) : (real)0;
         }
         if (!grid_barrier(&st->bar_count, epoch, &s_ok)) break;
         const real* rowp = P.rowp;
@@ -245,6 +257,9 @@ __global__ void __launch_bounds__(kSelBlock, 1) pivot_loop_kernel(PivotParams<re
             __threadfence_system();
             rowp = arena_rowp(P, P.rank, par);
             piv = __ldcg(rowp + stored_row(P, 1 + (long long)q));  // a_pq = T[1+q][p]
+            for (long long i = gtid; i < P.ld; i += gstride)
+                P.s[i] = (i < P.m_loc && i != lp) ? div_r(-__ldcg(P.col + i), piv) : (real)0;
+            if (!grid_barrier(&st->bar_count, epoch, &s_ok)) break;
         }
         const real sc = div_r(-cq, piv);  // src/solver.cu:54
         if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -254,7 +269,7 @@ __global__ void __launch_bounds__(kSelBlock, 1) pivot_loop_kernel(PivotParams<re
 
         // ---- phase D: cost update + next entering tournament, then the rank-1 update ----------------
         if (blockIdx.x < P.Gc) cost_select_blocks<real, true, true>(P, rowp, sc, sm, &s_flag);
-        stream_tiles<real, VB, U, 3, SKIP, true, true>(P, rowp, nullptr, P.col, piv, owner ? lp : -1, &s_next);
+        stream_phase<real, VB, U, SKIP>(P, rowp, &s_next);
         if (!grid_barrier(&st->bar_count, epoch, &s_ok)) break;
     }
 }

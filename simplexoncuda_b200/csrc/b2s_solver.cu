@@ -382,7 +382,16 @@ struct SolverImpl final : SolverBase {
         if (use_persistent()) v = 8;  // the loop kernel is built for the 256-bit / 8-row / ticketed geometry
         return table[v];
     }
-    bool use_persistent() const { return opt.persistent != 0 && (world == 1 || p2p); }
+    // persistent: 0 = three launches per pivot, 1 = loop kernel, 2 = auto.  Measured on B200 (profiles/
+    // r01_loop_modes.md): the loop kernel wins whenever the fixed cost of a pivot matters (L2-resident
+    // tableaux: 46k vs 30k pivots/s at 1024x1024; sharded slabs) and loses ~2 % when a pivot streams a
+    // gigabyte (8192x8192), where graph-replayed launches are already hidden.
+    bool use_persistent() const
+    {
+        if (opt.persistent == 0 || (world > 1 && !p2p)) return false;
+        if (opt.persistent == 1) return true;
+        return world > 1 || (double)Rs * (double)ld * sizeof(real) < 192e6;
+    }
     typedef void (*LoopFn)(PivotParams<real>, int);
     LoopFn loop_fn() const
     {
@@ -1305,7 +1314,7 @@ void b2s_default_options(b2s_options* opt)
     opt->max_pivots = 0;
     opt->trace_capacity = 0;
     opt->update_variant = 8;
-    opt->persistent = 1;
+    opt->persistent = 2;
 }
 
 int b2s_device_count(void)

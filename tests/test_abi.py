@@ -38,7 +38,7 @@ def test_struct_layouts():
     assert ctypes.sizeof(_lib.Stats) == 104
     opt = _lib.Options()
     _lib.load().b2s_default_options(ctypes.byref(opt))
-    assert (opt.dtype, opt.pivot_rule, opt.fold_artificials, opt.use_graph, opt.persistent) == (0, 0, 1, 1, 1)
+    assert (opt.dtype, opt.pivot_rule, opt.fold_artificials, opt.use_graph, opt.persistent) == (0, 0, 1, 1, 2)
 
 
 def test_seed_triplets_match_oracle():
