@@ -236,7 +236,7 @@ def run_b2s(a):
     dims = s.dims()
     elem = 8
     slab_bytes = dims["rows_stored"] * (m // world) * elem
-    persistent_on = a.loop == "persistent" or (a.loop == "auto" and (world > 1 or slab_bytes < 192e6))
+    persistent_on = a.loop == "persistent" or (a.loop == "auto" and world == 1 and slab_bytes < 192e6)
     loop_mode = ("persistent cooperative loop kernel (1 launch per batch of pivots)" if persistent_on
                  else "3 launches per pivot replayed as a CUDA graph")
     bytes_per_pivot = 2.0 * dims["rows_stored"] * (m // world) * elem  # per rank: read + write of the stored slab
@@ -300,7 +300,7 @@ def run_b2s(a):
                        "parallelism": f"constraint slabs x{world}" if world > 1 else "single GPU",
                        "skip_zero_rows": bool(a.skip_zero_rows), "update_variant": a.update_variant,
                        "loop": loop_mode},
-            "clocks": clocks, "gpu_launches": pivots if "persistent" in loop_mode else 3 * pivots + (pivots if world > 1 else 0), "wall_s_timed_region": wall}
+            "clocks": clocks, "gpu_launches": pivots if "persistent" in loop_mode else (3 if world == 1 else 2) * pivots, "wall_s_timed_region": wall}
     if rows_note is not None:
         line["config"]["rows_streamed_fraction"] = rows_note
     if roofline:

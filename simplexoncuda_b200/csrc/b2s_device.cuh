@@ -248,6 +248,7 @@ struct PivotParams {
     int world;
     long long arena_rows;          // capacity of one arena rowp buffer (elements)
     unsigned char* peers[kMaxPeers];
+    int fused_select;              // P2P: ratio_p2p_kernel also does exchange 2; update_kernel reads rowp from the arena
     // update-kernel tiling
     int log2_tpr;   // log2(threads per tableau row)
     int nchunks;    // column chunks per row
@@ -260,5 +261,34 @@ __device__ __forceinline__ long long stored_row(const PivotParams<real>& P, long
 {
     return cost_index >= P.fold_from ? cost_index - P.m : cost_index;
 }
+
+// ---- peer-memory arena of a sharded solve (see b2s_p2p.cuh) -----------------------------------
+template <typename real>
+struct ArenaHeader {
+    real slot_v[2][kMaxSlots];
+    real slot_max[2][kMaxSlots];
+    int slot_i[2][kMaxSlots];
+    int slot_k[2][kMaxSlots];
+    unsigned long long flag_slots[2][kMaxPeers];
+    unsigned long long flag_rowp[2];
+    unsigned long long pad[6];
+};
+
+template <typename real>
+__host__ __device__ inline size_t arena_bytes(long long rows)
+{
+    return sizeof(ArenaHeader<real>) + 2 * sizeof(real) * (size_t)rows;
+}
+template <typename real>
+__device__ __forceinline__ ArenaHeader<real>* arena_of(const PivotParams<real>& P, int r)
+{
+    return reinterpret_cast<ArenaHeader<real>*>(P.peers[r]);
+}
+template <typename real>
+__device__ __forceinline__ real* arena_rowp(const PivotParams<real>& P, int r, int parity)
+{
+    return reinterpret_cast<real*>(P.peers[r] + sizeof(ArenaHeader<real>)) + (size_t)parity * P.arena_rows;
+}
+
 
 }  // namespace b2s

@@ -457,9 +457,11 @@ __global__ void __launch_bounds__(kSelBlock, (VB * U <= 128) ? 2 : 1) update_ker
     __shared__ long long s_next;
     if (!__ldcg(&P.st->live)) return;
 
-    if (blockIdx.x < P.Gc) cost_select_blocks<real, true>(P, P.rowp, (real)__ldcg(&P.st->sc), sm, &s_flag);
+    // sharded + fused select: the pivot constraint sits in this rank's arena (parity of the pivot number)
+    const real* rowp = P.fused_select ? arena_rowp(P, P.rank, (int)(__ldcg(&P.st->pivots) & 1)) : P.rowp;
+    if (blockIdx.x < P.Gc) cost_select_blocks<real, true>(P, rowp, (real)__ldcg(&P.st->sc), sm, &s_flag);
 
-    stream_tiles<real, VB, U, HINT, SKIP, DYN, false>(P, P.rowp, P.s, nullptr, (real)0, -1, &s_next);
+    stream_tiles<real, VB, U, HINT, SKIP, DYN, false>(P, rowp, P.s, nullptr, (real)0, -1, &s_next);
     if (DYN) {
         // the last CTA to leave re-arms the ticket counters for the next launch
         if (threadIdx.x == 0) {

@@ -384,13 +384,13 @@ struct SolverImpl final : SolverBase {
     }
     // persistent: 0 = three launches per pivot, 1 = loop kernel, 2 = auto.  Measured on B200 (profiles/
     // r01_loop_modes.md): the loop kernel wins whenever the fixed cost of a pivot matters (L2-resident
-    // tableaux: 46k vs 30k pivots/s at 1024x1024; sharded slabs) and loses ~2 % when a pivot streams a
-    // gigabyte (8192x8192), where graph-replayed launches are already hidden.
+    // tableaux or slabs: 46k vs 30k pivots/s at 1024x1024) and loses 2-8 % when a pivot streams hundreds of
+    // megabytes per GPU (8192x8192 on 1 or 2 GPUs), where graph-replayed launches are already hidden.
     bool use_persistent() const
     {
         if (opt.persistent == 0 || (world > 1 && !p2p)) return false;
         if (opt.persistent == 1) return true;
-        return world > 1 || (double)Rs * (double)ld * sizeof(real) < 192e6;
+        return world == 1 && (double)Rs * (double)ld * sizeof(real) < 192e6;
     }
     typedef void (*LoopFn)(PivotParams<real>, int);
     LoopFn loop_fn() const
@@ -463,6 +463,11 @@ struct SolverImpl final : SolverBase {
         P.world = world;
         P.arena_rows = arena_rows;
         for (int r = 0; r < kMaxPeers; ++r) P.peers[r] = peer_ptr[r];
+        {
+            // one CTA gathers the pivot constraint when selection is fused: fine up to a few 100k rows
+            const char* e = getenv("B2S_FUSED_SELECT");
+            P.fused_select = (world > 1 && p2p && !use_persistent() && (e ? atoi(e) != 0 : Rs <= 300000)) ? 1 : 0;
+        }
         // update-kernel tiling
         const Variant v = variant();
         const int ept = v.vb / (int)sizeof(real);
@@ -680,8 +685,10 @@ struct SolverImpl final : SolverBase {
         if (world > 1 && p2p) {
             // exchanges done by the kernels themselves over NVLink peer memory (b2s_p2p.cuh)
             ratio_p2p_kernel<real><<<P.Gm_loc, kSelBlock, 0, stream>>>(P);
-            gather_p2p_kernel<real><<<(unsigned)((Rs + 255) / 256), 256, 0, stream>>>(P);
-            svec_p2p_kernel<real><<<(unsigned)((std::max(Rs, ld) + 255) / 256), 256, 0, stream>>>(P);
+            if (!P.fused_select) {
+                gather_p2p_kernel<real><<<(unsigned)((Rs + 255) / 256), 256, 0, stream>>>(P);
+                svec_p2p_kernel<real><<<(unsigned)((std::max(Rs, ld) + 255) / 256), 256, 0, stream>>>(P);
+            }
             update_fn()<<<upd_grid, kSelBlock, 0, stream>>>(P);
             return B2S_OK;
         }
