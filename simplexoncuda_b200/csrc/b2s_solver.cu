@@ -464,9 +464,11 @@ struct SolverImpl final : SolverBase {
         P.arena_rows = arena_rows;
         for (int r = 0; r < kMaxPeers; ++r) P.peers[r] = peer_ptr[r];
         {
-            // one CTA gathers the pivot constraint when selection is fused: fine up to a few 100k rows
+            // Experimental (B2S_FUSED_SELECT=1): one CTA does exchange 2 inside the select kernel, saving two
+            // launches per pivot.  Measured slower on B200 (4486 vs 5101 pivots/s at 8192x8192 on 2 GPUs: a
+            // single CTA cannot hide the latency of R strided gathers), so it is off by default.
             const char* e = getenv("B2S_FUSED_SELECT");
-            P.fused_select = (world > 1 && p2p && !use_persistent() && (e ? atoi(e) != 0 : Rs <= 300000)) ? 1 : 0;
+            P.fused_select = (world > 1 && p2p && !use_persistent() && e && atoi(e) != 0) ? 1 : 0;
         }
         // update-kernel tiling
         const Variant v = variant();
