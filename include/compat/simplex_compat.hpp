@@ -104,6 +104,14 @@ int twoPhaseMethod(problem_t* problem, TYPE* solution, TYPE* optimalValue);   //
 #ifdef TIMER
 void enableBenchmarkMode();    // reference include/twoPhaseMethod.h:21-24
 void disableBenchmarkMode();
+// TIMER is a compile-time switch of the reference (per-step CSV, src/chrono.cu); the shim library is built
+// once, so a program compiled with -D TIMER announces it at start-up and gets the same CSV files.
+void b2s_compat_timer_build();
+namespace {
+struct B2sTimerAnnounce {
+    B2sTimerAnnounce() { b2s_compat_timer_build(); }
+} b2s_timer_announce_;
+}  // namespace
 #endif
 
 // ---- reduction.cuh / gaussian.cuh ---------------------------------------------------------------------

@@ -52,6 +52,8 @@ bool g_benchmark = false;
 
 }  // namespace
 
+static FILE* g_csv = nullptr;  // TIMER CSV (chrono.cuh section below)
+
 // ---- error.cuh ------------------------------------------------------------------------------------
 void HandleError(cudaError_t err, const char* file, int line)
 {
@@ -130,34 +132,90 @@ void freeProblem(problem_t* problem)
 }
 
 // ---- twoPhaseMethod.h --------------------------------------------------------------------------------
+static bool g_timer_build = false;  // a translation unit of the program was compiled with -D TIMER
+void b2s_compat_timer_build() { g_timer_build = true; }
+static bool timer_on() { return g_timer_build || g_benchmark || getenv("B2S_TIMER") != nullptr; }
+
+// Pivot loop of one phase.  With the TIMER CSV enabled every iteration is timed on its own with CUDA events
+// (b2s_profile_pivots) and logged as one `solve` line, like the reference's -D TIMER build does around each
+// call of its per-iteration function (src/solver.cu:84-124); the last line is the terminating optimality check.
+static int run_phase(b2s_solver* h, tabular_t* shape)
+{
+    int st = B2S_RUNNING;
+    long long done = 0;
+    if (!timer_on()) {
+        must(b2s_iterate(h, -1, &st, &done));
+        return st;
+    }
+    const int chunk = 256;
+    std::vector<float> a(chunk), b(chunk), c(chunk);
+    while (true) {
+        must(b2s_profile_pivots(h, chunk, a.data(), b.data(), c.data(), &done));
+        for (long long k = 0; k < done; ++k)
+            fprintf(g_csv, "%d,%d,solve,%f\n", shape->rows, shape->cols, (double)(a[k] + b[k] + c[k]) * 1000.0);
+        if (done < chunk) break;
+    }
+    start(shape, "solve");  // the iteration that finds no entering column (or an unbounded one)
+    must(b2s_iterate(h, 0, &st, &done));
+    stop();
+    must(b2s_iterate(h, -1, &st, &done));  // state is final already: returns the phase status
+    return st;
+}
+
 int twoPhaseMethod(problem_t* problem, TYPE* solution, TYPE* optimalValue)
 {
     b2s_solver* h = handle();
+    const bool timed = timer_on();
+    tabular_t shape;  // only rows/cols are used, by the CSV lines
+    memset(&shape, 0, sizeof(shape));
+    shape.cols = problem->constraints;
+    shape.rows = 1 + problem->vars + 2 * problem->constraints;
+    if (timed) {
+        if (g_benchmark)
+            initCsvBenchmark(problem->vars, problem->constraints);
+        else
+            initCsv();
+    }
     // the reference's progress lines (src/twoPhaseMethod.cu:228,243,257,296,333,347)
     printf("Phase 1: Filling Tableau\n");
+    if (timed) start(&shape, "fillTableau");
     must(b2s_load_problem_host(h, problem->vars, problem->constraints, problem->constraintsMatrix,
                                problem->knownTermsVector, problem->objectiveFunction));
     must(b2s_build_phase1(h));
+    if (timed) stop();
     printf("Phase 1: Resetting out-of-base variables\n");
+    if (timed) start(&shape, "gauss1");
     must(b2s_price_out(h));
+    if (timed) stop();
     printf("Phase 1: Solving auxiliary problem\n");
     must(b2s_select_entering(h));
-    int st = B2S_RUNNING;
-    long long done = 0;
-    must(b2s_iterate(h, -1, &st, &done));
+    run_phase(h, &shape);  // the phase-1 status is ignored by the reference too (src/twoPhaseMethod.cu:258)
     int verdict = FEASIBLE;
+    if (timed) start(&shape, "checkDegeneracy");
     must(b2s_phase1_verdict(h, &verdict));
-    if (verdict != FEASIBLE) return verdict;
-    printf("Phase 2: Filling costs vector with the original one\n");
-    must(b2s_switch_phase2(h));
-    printf("Phase 2: Resetting out-of-base variables\n");
-    must(b2s_price_out(h));
-    printf("Phase 2: Solving original problem\n");
-    must(b2s_select_entering(h));
-    must(b2s_iterate(h, -1, &st, &done));
-    if (st != FEASIBLE) return st;
-    must(b2s_extract_solution(h, solution, optimalValue));
-    return FEASIBLE;
+    if (timed) stop();
+    int result = verdict;
+    if (verdict == FEASIBLE) {
+        shape.rows -= shape.cols;  // src/twoPhaseMethod.cu:288
+        printf("Phase 2: Filling costs vector with the original one\n");
+        if (timed) start(&shape, "costsVector");
+        must(b2s_switch_phase2(h));
+        if (timed) stop();
+        printf("Phase 2: Resetting out-of-base variables\n");
+        if (timed) start(&shape, "gauss2");
+        must(b2s_price_out(h));
+        if (timed) stop();
+        printf("Phase 2: Solving original problem\n");
+        must(b2s_select_entering(h));
+        result = run_phase(h, &shape);
+        if (result == FEASIBLE) {
+            if (timed) start(&shape, "solution");
+            must(b2s_extract_solution(h, solution, optimalValue));
+            if (timed) stop();
+        }
+    }
+    if (timed) closeCsv();
+    return result;
 }
 
 void enableBenchmarkMode() { g_benchmark = true; }
@@ -296,7 +354,6 @@ cudaStream_t* generateMatrixInParallelAsync(TYPE* dst, int width, int height, un
 }
 
 // ---- chrono.cuh: the reference's TIMER CSV (src/chrono.cu:8-56), same file naming and line format ----------
-static FILE* g_csv = nullptr;
 static cudaEvent_t g_ev0, g_ev1;
 
 static void open_csv(const char* name)

@@ -62,3 +62,29 @@ def test_random_flag(tmp_path):
         s_ref, sol_ref, _ = run(REF, str(tmp_path / f"ref{seed}"), ["-r", "64", "48", str(seed)])
         s_our, sol_our, _ = run(OURS, str(tmp_path / f"ours{seed}"), ["-r", "64", "48", str(seed)])
         assert s_ref == s_our and sol_ref == sol_our
+
+
+def _csv_counts(cwd):
+    """{(rows, operation): count} of the TIMER CSV the program wrote into cwd (src/chrono.cu:8-22 naming)."""
+    files = [f for f in os.listdir(cwd) if f.startswith("..\\data\\measures\\times_")]
+    assert len(files) == 1, files
+    counts = {}
+    for ln in open(os.path.join(cwd, files[0])).read().splitlines()[1:]:
+        rows, cols, op, us = ln.split(",")
+        float(us)
+        counts[(int(rows), op)] = counts.get((int(rows), op), 0) + 1
+    return counts
+
+
+@needs
+@pytest.mark.parametrize("n,m,seed", [(256, 256, 25856), (512, 256, 51456)])
+def test_timer_csv_matches_reference(tmp_path, n, m, seed):
+    """Both programs are -D TIMER builds: same CSV file naming, same operations, and the same number of `solve`
+    lines per phase (= pivots + 1), which is how the reference's published pivot counts were recorded."""
+    sf = tmp_path / "seed.txt"
+    sf.write_text(f"{n} {m} {seed} 1 100")
+    run(REF, str(tmp_path / "ref"), ["-rf", str(sf)])
+    run(OURS, str(tmp_path / "ours"), ["-rf", str(sf)])
+    ref, ours = _csv_counts(str(tmp_path / "ref")), _csv_counts(str(tmp_path / "ours"))
+    assert ref == ours
+    assert ours[(1 + n + 2 * m, "solve")] > 1 and ours[(1 + n + m, "solve")] > 1
