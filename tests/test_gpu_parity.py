@@ -187,7 +187,7 @@ def _grid(max_cons):
             yield inst
 
 
-@pytest.mark.parametrize("inst", list(_grid(2048)), ids=lambda i: f"{i['vars']}x{i['constraints']}")
+@pytest.mark.parametrize("inst", list(_grid(8192)), ids=lambda i: f"{i['vars']}x{i['constraints']}")
 def test_published_grid(S, inst):
     """Device-generated instance (MSVC seed flavour) -> published pivot counts of the reference, and the
     oracle's pivot-sequence hash / objective from the committed fixture."""
@@ -263,3 +263,31 @@ def test_fp32_generator_and_examples(S):
         assert st == EXAMPLES[name]["status"]
         if st == 0:
             assert abs(obj - EXAMPLES[name]["objective"]) <= 1e-4 * EXAMPLES[name]["objective"]
+
+
+def test_solver_handle_is_reusable(S):
+    """One handle, several problems of different shapes (buffers grow and shrink), results unaffected."""
+    with S.Solver() as s:
+        for n, m, seed, lo in ((40, 24, 3, -100), (600, 520, 11, 1), (64, 64, 5, 1), (40, 24, 3, -100)):
+            A, b, c = O.generate(n, m, O.seed_triplet(seed, 0), lo, 100)
+            ref = O.Oracle(A, b, c).two_phase()
+            s.load(A, b, c)
+            r = s.solve()
+            assert r["status"] == ref["status"] and int(r["stats"].trace_hash) == ref["hash"]
+            if ref["status"] == 0:
+                assert r["objective"] == ref["objective"]
+
+
+def test_call_order_errors(S):
+    with S.Solver() as s:
+        with pytest.raises(S.B2SError):
+            s.build_phase1()                       # nothing loaded
+        A, b, c = O.generate(8, 6, (1, 2, 3), 1, 100)
+        s.load(A, b, c)
+        with pytest.raises(S.B2SError):
+            s.iterate(1)                           # not built / priced / selected yet
+        s.build_phase1()
+        with pytest.raises(S.B2SError):
+            s.select_entering()                    # price-out first
+    with pytest.raises(S.B2SError):
+        S.Solver(pivot_rule=7)
