@@ -223,7 +223,7 @@ struct SolverImpl final : SolverBase {
         CK(cudaEventCreate(&ev0));
         CK(cudaEventCreate(&ev1));
         CK(cudaMalloc(&st, sizeof(DevState)));
-        CK(cudaMemset(st, 0, sizeof(DevState)));
+        CK(cudaMemsetAsync(st, 0, sizeof(DevState), stream));  // `stream` is non-blocking: never mix in legacy-stream calls
         CK(cudaHostAlloc(&st_host, 3 * sizeof(DevState), cudaHostAllocDefault));
         CK(cudaEventCreateWithFlags(&poll_ev[0], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&poll_ev[1], cudaEventDisableTiming));
@@ -268,16 +268,17 @@ struct SolverImpl final : SolverBase {
         close_arena();
         const long long cap = (rows + 1023) / 1024 * 1024;
         CK(cudaMalloc(&arena, arena_bytes<real>(cap)));
-        CK(cudaMemset(arena, 0, arena_bytes<real>(cap)));
+        CK(cudaMemsetAsync(arena, 0, arena_bytes<real>(cap), stream));
         cudaIpcMemHandle_t mine;
         CK(cudaIpcGetMemHandle(&mine, arena));
         unsigned char* hbuf = nullptr;
         CK(cudaMalloc(&hbuf, sizeof(mine) * (size_t)world));
-        CK(cudaMemcpy(hbuf + sizeof(mine) * (size_t)rank, &mine, sizeof(mine), cudaMemcpyHostToDevice));
+        CK(cudaMemcpyAsync(hbuf + sizeof(mine) * (size_t)rank, &mine, sizeof(mine), cudaMemcpyHostToDevice, stream));
         NK(ncclAllGather(hbuf + sizeof(mine) * (size_t)rank, hbuf, sizeof(mine), ncclChar, comm, stream));
         CK(cudaStreamSynchronize(stream));
         std::vector<cudaIpcMemHandle_t> all((size_t)world);
-        CK(cudaMemcpy(all.data(), hbuf, sizeof(mine) * (size_t)world, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpyAsync(all.data(), hbuf, sizeof(mine) * (size_t)world, cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
         cudaFree(hbuf);
         for (int r = 0; r < world; ++r) {
             if (r == rank) {
@@ -562,7 +563,8 @@ struct SolverImpl final : SolverBase {
         std::vector<uint32_t> host;
         xorwow_build_jump_tables(host);
         CK(cudaMalloc(&jump_tables, host.size() * sizeof(uint32_t)));
-        CK(cudaMemcpy(jump_tables, host.data(), host.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        CK(cudaMemcpyAsync(jump_tables, host.data(), host.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+        CK(cudaStreamSynchronize(stream));  // `host` goes out of scope
         return B2S_OK;
     }
 
@@ -602,19 +604,21 @@ struct SolverImpl final : SolverBase {
         CK(cudaSetDevice(dev));
         if (sizeof(real) == sizeof(double)) {
             if (A)
-                CK(cudaMemcpy2D(A, sizeof(double) * m, T + ld, sizeof(real) * ld, sizeof(double) * m, (size_t)n,
-                                cudaMemcpyDeviceToHost));
-            if (b) CK(cudaMemcpy(b, T, sizeof(double) * m, cudaMemcpyDeviceToHost));
-            if (c) CK(cudaMemcpy(c, c_dev, sizeof(double) * n, cudaMemcpyDeviceToHost));
+                CK(cudaMemcpy2DAsync(A, sizeof(double) * m, T + ld, sizeof(real) * ld, sizeof(double) * m, (size_t)n,
+                                     cudaMemcpyDeviceToHost, stream));
+            if (b) CK(cudaMemcpyAsync(b, T, sizeof(double) * m, cudaMemcpyDeviceToHost, stream));
+            if (c) CK(cudaMemcpyAsync(c, c_dev, sizeof(double) * n, cudaMemcpyDeviceToHost, stream));
+            CK(cudaStreamSynchronize(stream));
         } else {
             int rc = ensure_stage((size_t)(n + 1) * (size_t)m + (size_t)n);
             if (rc) return rc;
             widen_rows<<<1024, 256, 0, stream>>>(stage_dev, (long long)m, T, ld, (long long)(n + 1), m);
             widen_rows<<<64, 256, 0, stream>>>(stage_dev + (size_t)(n + 1) * m, (long long)n, c_dev, (long long)n, 1ll, n);
             CK(cudaStreamSynchronize(stream));
-            if (b) CK(cudaMemcpy(b, stage_dev, sizeof(double) * m, cudaMemcpyDeviceToHost));
-            if (A) CK(cudaMemcpy(A, stage_dev + m, sizeof(double) * (size_t)n * m, cudaMemcpyDeviceToHost));
-            if (c) CK(cudaMemcpy(c, stage_dev + (size_t)(n + 1) * m, sizeof(double) * n, cudaMemcpyDeviceToHost));
+            if (b) CK(cudaMemcpyAsync(b, stage_dev, sizeof(double) * m, cudaMemcpyDeviceToHost, stream));
+            if (A) CK(cudaMemcpyAsync(A, stage_dev + m, sizeof(double) * (size_t)n * m, cudaMemcpyDeviceToHost, stream));
+            if (c) CK(cudaMemcpyAsync(c, stage_dev + (size_t)(n + 1) * m, sizeof(double) * n, cudaMemcpyDeviceToHost, stream));
+            CK(cudaStreamSynchronize(stream));
         }
         return B2S_OK;
     }
@@ -1174,8 +1178,8 @@ struct SolverImpl final : SolverBase {
         CK(cudaMalloc(&di, sizeof(int) * kMaxSlots));
         CK(cudaMalloc(&dk, sizeof(int) * kMaxSlots));
         CK(cudaMalloc(&dst, sizeof(DevState)));
-        CK(cudaMemset(dst, 0, sizeof(DevState)));
-        CK(cudaMemcpy(dcost, h.data(), sizeof(real) * ((size_t)cnt + 1), cudaMemcpyHostToDevice));
+        CK(cudaMemsetAsync(dst, 0, sizeof(DevState), stream));
+        CK(cudaMemcpyAsync(dcost, h.data(), sizeof(real) * ((size_t)cnt + 1), cudaMemcpyHostToDevice, stream));
         PivotParams<real> Q{};
         Q.cost = dcost;
         Q.Rc = cnt + 1;

@@ -29,4 +29,7 @@ FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -fmad=fa
     -L"$NCCL_LIB" -l:libnccl.so.2 -Xlinker -rpath,"$NCCL_LIB"
 "$NVCC" -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -fmad=false -Xcompiler -fPIC,-O2,-ffp-contract=off \
     -shared -o "$OUT/libb2s_compat.so" "$HERE/compat.cu" -L"$OUT" -lb2s -Xlinker -rpath,'$ORIGIN'
-echo "built $OUT/libb2s.so $OUT/libb2s_compat.so"
+# C++ client of the tabular_t-level drop-in API (used by tests/test_tabular_level.py on the GPU box)
+"$NVCC" -gencode arch=compute_100a,code=sm_100a -O2 -std=c++17 -I"$HERE/../../include/compat" \
+    -o "$OUT/test_tabular_level" "$HERE/../../tests/cpp/tabular_level.cu" -L"$OUT" -lb2s_compat -lb2s -Xlinker -rpath,'$ORIGIN'
+echo "built $OUT/libb2s.so $OUT/libb2s_compat.so $OUT/test_tabular_level"

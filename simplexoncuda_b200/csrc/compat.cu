@@ -230,6 +230,7 @@ tabular_t* newTabular(problem_t* problem)  // src/tabular.cu:25-39 (zero-filled 
     t->rows = 1 + problem->vars + 2 * problem->constraints;
     HANDLE_ERROR(cudaMallocPitch((void**)&t->table, &t->pitch, sizeof(TYPE) * (size_t)t->cols, (size_t)t->rows));
     HANDLE_ERROR(cudaMemset2D(t->table, t->pitch, 0, t->pitch, (size_t)t->rows));
+    HANDLE_ERROR(cudaDeviceSynchronize());
     HANDLE_ERROR(cudaMalloc((void**)&t->costsVector, sizeof(TYPE) * (size_t)t->rows));
     t->knownTermsVector = t->table;
     t->constraintsMatrix = ROW(t->table, 1, t->pitch);
@@ -265,6 +266,8 @@ void printTableauToStream(FILE* Stream, tabular_t* tabular, int* base)  // src/t
 // ---- solver.h / gaussian.cuh / reduction.cuh on a caller-owned tabular_t --------------------------------
 static void attach(tabular_t* t, int* base)
 {
+    // the caller filled the tableau on its own streams; the solver works on a private non-blocking stream
+    HANDLE_ERROR(cudaDeviceSynchronize());
     must(b2s_attach_tableau_device(handle(), t->table, t->pitch, t->rows, t->cols, t->costsVector, t->problem->vars));
     must(b2s_set_basis(handle(), base));
 }
@@ -290,6 +293,7 @@ void updateObjectiveFunction(tabular_t* tabular, int* base)  // src/gaussian.cu:
 TYPE minElement(TYPE* g_vet, unsigned int size, unsigned int* outIndex)
 {
     double v = 0;
+    HANDLE_ERROR(cudaDeviceSynchronize());
     must(b2s_min_element_device(handle(), g_vet, size, &v, outIndex));
     return v;
 }
@@ -297,6 +301,7 @@ TYPE minElement(TYPE* g_vet, unsigned int size, unsigned int* outIndex)
 TYPE minElement(TYPE* knownTerms, TYPE* rowPivot, unsigned int size, unsigned int* outIndex)
 {
     double v = 0;
+    HANDLE_ERROR(cudaDeviceSynchronize());
     must(b2s_ratio_min_device(handle(), knownTerms, rowPivot, size, &v, outIndex));
     return v;
 }
@@ -304,6 +309,7 @@ TYPE minElement(TYPE* knownTerms, TYPE* rowPivot, unsigned int size, unsigned in
 bool isLessOrEqualThanZero(TYPE* g_vet, unsigned int size)
 {
     int r = 0;
+    HANDLE_ERROR(cudaDeviceSynchronize());
     must(b2s_max_le_zero_device(handle(), g_vet, size, &r));
     return r != 0;
 }
@@ -317,6 +323,7 @@ static const uint32_t* jump_tables()
         b2s::xorwow_build_jump_tables(host);
         HANDLE_ERROR(cudaMalloc(&dev, host.size() * sizeof(uint32_t)));
         HANDLE_ERROR(cudaMemcpy(dev, host.data(), host.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        HANDLE_ERROR(cudaDeviceSynchronize());  // consumers run on other (possibly non-blocking) streams
     }
     return dev;
 }
