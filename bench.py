@@ -55,6 +55,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-pivots", type=int, default=0, help="pivot budget of the cpu_baseline sample (0 = auto)")
     ap.add_argument("--skip-zero-rows", action="store_true")
+    ap.add_argument("--no-large-config", dest="large_config", action="store_false",
+                    help="skip the supplementary 65536x65536 measurement")
     ap.add_argument("--update-variant", type=int, default=8)
     ap.add_argument("--loop", default="auto", choices=["auto", "persistent", "launches"],
                     help="persistent cooperative loop kernel, three launches per pivot (CUDA graph), or the library's choice")
@@ -340,6 +342,37 @@ def run_b2s(a):
                                "the instance only ever exists on the devices"}
     if not a.no_cpu_baseline and rank == 0 and world == 1:
         line["cpu_baseline"] = cpu_baseline(a)
+
+    # ---- supplementary: BASELINE.json configs[4], the sharded shape (65536 x 131072 fp64, 68.7 GB tableau) ----
+    # Same protocol as `value` on a short pivot budget; generated on the devices (its constraint matrix alone is
+    # 34 GB).  Not part of `value`: it documents the north star's "near-linear scaling at 65536 x 131072".
+    if a.large_config and (n, m) == (8192, 8192):
+        try:
+            ln = lm = 65536
+            g = S.Solver(device=local, update_variant=a.update_variant)
+            if world > 1:
+                sharding.init_sharded_solver(g, dist)
+            g.generate(ln, lm, S.seed_triplet(ln * 100 + lm, S.RAND_MSVC), 1, 100)
+            g.build_phase1(); g.price_out(); g.select_entering()
+            ldims = g.dims()
+            g.iterate(5)
+            barrier()
+            before = g.stats().seconds_phase1
+            st_l, done_l = g.iterate(20)
+            barrier()
+            ms_l = torch.tensor([(g.stats().seconds_phase1 - before) * 1e3], dtype=torch.float64, device="cuda")
+            if dist is not None:
+                dist.all_reduce(ms_l, op=dist.ReduceOp.MAX)
+            g.close()
+            pps = done_l / (float(ms_l.item()) * 1e-3)
+            slab = 2.0 * ldims["rows_stored"] * (lm // world) * elem
+            line["large_config"] = {"workload": "random_65536_65536 (seed 6619136, [1,100]); tableau 65536x131072 fp64, "
+                                                f"{ldims['rows_stored'] * lm * elem / 1e9:.1f} GB, constraint slabs x{world}",
+                                    "pivots_per_s": pps, "pivots_timed": done_l,
+                                    "per_gpu_stream_GBps": slab * pps / 1e9,
+                                    "frac_of_measured_hbm_peak": slab * pps / 1e9 / peaks()[0]}
+        except Exception as exc:  # e.g. not enough free HBM on a shared box
+            line["large_config"] = {"skipped": str(exc)[:200]}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if dist is not None:
