@@ -160,7 +160,7 @@ def run_reference(a):
         return 0
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     ref_lib = os.path.join(ROOT, "oracle", "_ref", "libsimplex_ref.so")
-    have_gpu_ref = os.path.exists(ref_lib)
+    have_gpu_ref = os.path.exists(ref_lib) and not os.environ.get("B2S_BENCH_FORCE_PORT")
     line = {"impl": "reference", "metric": METRIC, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(a), "pivots_per_step": a.pivots_per_step}}
@@ -342,6 +342,23 @@ def run_b2s(a):
                                "the instance only ever exists on the devices"}
     if not a.no_cpu_baseline and rank == 0 and world == 1:
         line["cpu_baseline"] = cpu_baseline(a)
+
+    # ---- supplementary: the same complete solve with skip_zero_rows (opt-in, value-exact): rows whose pivot-
+    # constraint entry is exactly 0 are not streamed.  Reported apart so that `value`, `e2e` and `roofline` above
+    # keep the full 2*R*m*8 bytes per pivot.
+    if world == 1 and not a.no_e2e and not a.skip_zero_rows and n * m * 8 <= 8e9:
+        with S.Solver(device=local, skip_zero_rows=True, update_variant=a.update_variant,
+                      persistent={"auto": "auto", "persistent": True, "launches": False}[a.loop]) as z:
+            torch.cuda.synchronize()
+            t0 = time.time()
+            z.load(Ap.numpy(), bp.numpy(), cp.numpy())
+            rz = z.solve()
+            t1 = time.time()
+        pz = rz["stats"].pivots_phase1 + rz["stats"].pivots_phase2
+        line["skip_zero_rows"] = {"e2e_pivots_per_s": pz / (t1 - t0), "seconds": t1 - t0,
+                                  "rows_streamed_fraction": rz["stats"].rows_streamed / max(1, rz["stats"].rows_total),
+                                  "same_pivot_sequence": int(rz["stats"].trace_hash) == int(r["stats"].trace_hash),
+                                  "same_objective": rz["objective"] == r["objective"]}
 
     # ---- supplementary: BASELINE.json configs[4], the sharded shape (65536 x 131072 fp64, 68.7 GB tableau) ----
     # Same protocol as `value` on a short pivot budget; generated on the devices (its constraint matrix alone is
