@@ -484,7 +484,7 @@ struct SolverImpl final : SolverBase {
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, update_fn(), kSelBlock, 0);
         occ = std::max(1, occ);
         int grid = num_sms * occ;
-        if (P.nchunks <= grid) grid = grid / P.nchunks * P.nchunks;
+        if (!v.dyn && P.nchunks <= grid) grid = grid / P.nchunks * P.nchunks;  // static striding keeps a CTA on one chunk
         int tg = 4;
         for (; tg > 1; tg >>= 1) {
             const long long rows_tile = (long long)rpp * v.u * tg;
