@@ -31,6 +31,13 @@ constexpr int kSelBlock = 512;   // reference stage-1 block size (src/reduction.
 constexpr int kMaxSlots = 1024;  // reference stage-1 grid cap  (src/reduction.cu:7)
 constexpr int kMaxPeers = 8;     // GPUs of one box
 
+// Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-stream-serialization
+// attribute may start while its predecessor drains; it must call pdl_wait() before touching anything the
+// predecessor wrote.  pdl_trigger() lets the successor's CTAs be scheduled as soon as SM resources free up.
+// Both are no-ops for ordinary launches.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // Device-resident loop state: the host only polls it between batches of pivots.
 struct DevState {
     int status;       // kRunning until a phase ends (kFeasible = optimal, kUnbounded)

@@ -226,6 +226,8 @@ __global__ void __launch_bounds__(kSelBlock) ratio_kernel(PivotParams<real> P)
     __shared__ TreeSmem<real> sm;
     __shared__ real smax[32];
     __shared__ int s_flag;
+    pdl_wait();
+    pdl_trigger();
     DevState* st = P.st;
     const int status = __ldcg(&st->status);
     const long long pivots = __ldcg(&st->pivots), limit = __ldcg(&st->limit);
@@ -298,6 +300,8 @@ __global__ void __launch_bounds__(kSelBlock) ratio_finish_kernel(PivotParams<rea
 template <typename real, bool kSharded>
 __global__ void __launch_bounds__(256) gather_kernel(PivotParams<real> P)
 {
+    pdl_wait();
+    pdl_trigger();
     DevState* st = P.st;
     if (!__ldcg(&st->live)) return;
     const int p = __ldcg(&st->p);
@@ -455,6 +459,8 @@ __global__ void __launch_bounds__(kSelBlock, (VB * U <= 128) ? 2 : 1) update_ker
     __shared__ TreeSmem<real> sm;
     __shared__ int s_flag;
     __shared__ long long s_next;
+    pdl_wait();
+    pdl_trigger();  // the next pivot's ratio CTAs may take the SMs this grid frees while it drains
     if (!__ldcg(&P.st->live)) return;
 
     // sharded + fused select: the pivot constraint sits in this rank's arena (parity of the pivot number)

@@ -141,6 +141,7 @@ struct SolverImpl final : SolverBase {
     ncclComm_t comm = nullptr;
 #endif
     // peer-memory exchange (b2s_p2p.cuh)
+    bool use_pdl = false;          // single-GPU launches path: programmatic dependent launch between the 3 kernels
     bool p2p = false;              // arenas mapped on every rank: the per-pivot exchanges bypass NCCL
     unsigned char* arena = nullptr;
     long long arena_rows = 0;
@@ -231,6 +232,7 @@ struct SolverImpl final : SolverBase {
         trace_cap = opt.trace_capacity > 0 ? opt.trace_capacity : (1ll << 20);
         CK(cudaMalloc(&trace, sizeof(int2) * (size_t)trace_cap));
         folded = opt.fold_artificials != 0;
+        if (const char* e = getenv("B2S_PDL")) use_pdl = atoi(e) != 0;
         return B2S_OK;
     }
 
@@ -701,10 +703,35 @@ struct SolverImpl final : SolverBase {
 #ifdef B2S_WITH_NCCL
         if (world > 1) return enqueue_pivot_sharded();
 #endif
-        ratio_kernel<real, false><<<P.Gm, kSelBlock, 0, stream>>>(P);
         const long long work = std::max(Rs, ld);
+        if (use_pdl) {
+            // programmatic dependent launch: each kernel may be scheduled while its predecessor drains and
+            // blocks in griddepcontrol.wait until that predecessor's memory is visible
+            int rc;
+            if ((rc = launch_pdl((const void*)ratio_kernel<real, false>, (unsigned)P.Gm, kSelBlock))) return rc;
+            if ((rc = launch_pdl((const void*)gather_kernel<real, false>, (unsigned)((work + 255) / 256), 256))) return rc;
+            return launch_pdl((const void*)update_fn(), (unsigned)upd_grid, kSelBlock);
+        }
+        ratio_kernel<real, false><<<P.Gm, kSelBlock, 0, stream>>>(P);
         gather_kernel<real, false><<<(unsigned)((work + 255) / 256), 256, 0, stream>>>(P);
         update_fn()<<<upd_grid, kSelBlock, 0, stream>>>(P);
+        return B2S_OK;
+    }
+
+    int launch_pdl(const void* fn, unsigned grid, unsigned block)
+    {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(block);
+        cfg.dynamicSmemBytes = 0;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        void* args[] = {&P};
+        CK(cudaLaunchKernelExC(&cfg, fn, args));
         return B2S_OK;
     }
 
