@@ -306,6 +306,8 @@ struct SolverImpl final : SolverBase {
         CK(cudaSetDevice(dev));
         if (world > 1 && (m_ % (world * kSelBlock)) != 0)
             return fail(B2S_ERR_ARG, "sharded solve needs constraints %% (world*512) == 0 (m=%d, world=%d)", m_, world);
+        if (world > 1 && (long long)m_ > (long long)kSelBlock * kMaxSlots)
+            return fail(B2S_ERR_ARG, "sharded solve supports at most %d constraints", kSelBlock * kMaxSlots);
         n = n_;
         m = m_;
         m_loc = m / world;
@@ -778,8 +780,16 @@ struct SolverImpl final : SolverBase {
             PivotParams<real> Pk = P;
             int bk = batch;
             void* args[] = {&Pk, &bk};
-            CK(cudaLaunchCooperativeKernel((const void*)loop_fn(), dim3((unsigned)loop_grid), dim3(kSelBlock), args, 0, stream));
-            return B2S_OK;
+            cudaError_t ce = cudaLaunchCooperativeKernel((const void*)loop_fn(), dim3((unsigned)loop_grid), dim3(kSelBlock),
+                                                         args, 0, stream);
+            if (ce == cudaSuccess) return B2S_OK;
+            if (ce != cudaErrorCooperativeLaunchTooLarge && ce != cudaErrorLaunchOutOfResources)
+                return fail(B2S_ERR_CUDA, "cooperative launch of the pivot loop kernel: %s", cudaGetErrorString(ce));
+            // the SMs cannot host one CTA each right now (another context holds resources): use the other GPU
+            // loop body from here on -- same kernels' arithmetic, three launches per pivot
+            cudaGetLastError();
+            opt.persistent = 0;
+            fill_params();
         }
         const bool graphable = opt.use_graph && (world == 1 || p2p);
         if (!graphable) {
