@@ -255,7 +255,6 @@ struct PivotParams {
     int world;
     long long arena_rows;          // capacity of one arena rowp buffer (elements)
     unsigned char* peers[kMaxPeers];
-    int fused_select;              // P2P: ratio_p2p_kernel also does exchange 2; update_kernel reads rowp from the arena
     // update-kernel tiling
     int log2_tpr;   // log2(threads per tableau row)
     int nchunks;    // column chunks per row

@@ -463,8 +463,7 @@ __global__ void __launch_bounds__(kSelBlock, (VB * U <= 128) ? 2 : 1) update_ker
     pdl_trigger();  // the next pivot's ratio CTAs may take the SMs this grid frees while it drains
     if (!__ldcg(&P.st->live)) return;
 
-    // sharded + fused select: the pivot constraint sits in this rank's arena (parity of the pivot number)
-    const real* rowp = P.fused_select ? arena_rowp(P, P.rank, (int)(__ldcg(&P.st->pivots) & 1)) : P.rowp;
+    const real* rowp = P.rowp;
     if (blockIdx.x < P.Gc) cost_select_blocks<real, true>(P, rowp, (real)__ldcg(&P.st->sc), sm, &s_flag);
 
     stream_tiles<real, VB, U, HINT, SKIP, DYN, false>(P, rowp, P.s, nullptr, (real)0, -1, &s_next);

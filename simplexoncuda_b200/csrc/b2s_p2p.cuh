@@ -132,54 +132,6 @@ __global__ void __launch_bounds__(kSelBlock) ratio_p2p_kernel(PivotParams<real> 
     __threadfence_system();
     const ArenaHeader<real>* mine = arena_of(P, P.rank);
     ratio_finish(P, mine->slot_v[par], mine->slot_i[par], mine->slot_k[par], mine->slot_max[par], sm, smax);
-    if (!P.fused_select) return;  // exchange 2 then runs in gather_p2p_kernel / svec_p2p_kernel
-
-    // ---- fused exchange 2: this CTA (the last one of the rank) finishes the whole selection, so a pivot is
-    // two launches: select (this kernel) and update_kernel, which reads the pivot constraint from the arena.
-    __syncthreads();
-    if (!*(volatile int*)&st->live) return;  // unbounded: ratio_finish has set the status
-    const int p = *(volatile int*)&st->p;
-    const long long lp = (long long)p - P.col0;
-    if (lp >= 0 && lp < P.m_loc) {  // owner: gather the raw pivot constraint into every arena, normalise the column
-        const real pivl = __ldcg(P.col + lp);
-        for (long long r0 = threadIdx.x; r0 < P.Rs; r0 += 4 * kSelBlock) {
-            real a[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const long long r = r0 + (long long)u * kSelBlock;
-                a[u] = (r < P.Rs) ? __ldcg(P.T + r * P.ld + lp) : (real)0;
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const long long r = r0 + (long long)u * kSelBlock;
-                if (r < P.Rs) {
-                    P.T[r * P.ld + lp] = div_r(a[u], pivl);
-                    for (int w = 0; w < P.world; ++w) arena_rowp(P, w, par)[r] = a[u];
-                }
-            }
-        }
-        __threadfence_system();
-        __syncthreads();
-        if (threadIdx.x < P.world) st_release_sys(&arena_of(P, threadIdx.x)->flag_rowp[par], seq);
-    }
-    if (threadIdx.x == 0) s_flag = wait_flag(&arena_of(P, P.rank)->flag_rowp[par], seq) ? 1 : 0;
-    __syncthreads();
-    if (!s_flag) {
-        if (threadIdx.x == 0) {
-            st->status = kStatusPeerTimeout;
-            st->live = 0;
-        }
-        return;
-    }
-    __threadfence_system();
-    const real* rowp = arena_rowp(P, P.rank, par);
-    const real piv = __ldcg(rowp + stored_row(P, 1 + (long long)q));
-    for (long long i = threadIdx.x; i < P.ld; i += kSelBlock)
-        P.s[i] = (i < P.m_loc && i != lp) ? div_r(-__ldcg(P.col + i), piv) : (real)0;
-    if (threadIdx.x == 0) {
-        st->piv = (double)piv;
-        st->sc = (double)div_r((real)(-st->cq), piv);
-    }
 }
 
 // ---- exchange 2, owner side ----------------------------------------------------------------------

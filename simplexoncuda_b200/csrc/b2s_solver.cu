@@ -468,13 +468,6 @@ struct SolverImpl final : SolverBase {
         P.world = world;
         P.arena_rows = arena_rows;
         for (int r = 0; r < kMaxPeers; ++r) P.peers[r] = peer_ptr[r];
-        {
-            // Experimental (B2S_FUSED_SELECT=1): one CTA does exchange 2 inside the select kernel, saving two
-            // launches per pivot.  Measured slower on B200 (4486 vs 5101 pivots/s at 8192x8192 on 2 GPUs: a
-            // single CTA cannot hide the latency of R strided gathers), so it is off by default.
-            const char* e = getenv("B2S_FUSED_SELECT");
-            P.fused_select = (world > 1 && p2p && !use_persistent() && e && atoi(e) != 0) ? 1 : 0;
-        }
         // update-kernel tiling
         const Variant v = variant();
         const int ept = v.vb / (int)sizeof(real);
@@ -695,10 +688,8 @@ struct SolverImpl final : SolverBase {
         if (world > 1 && p2p) {
             // exchanges done by the kernels themselves over NVLink peer memory (b2s_p2p.cuh)
             ratio_p2p_kernel<real><<<P.Gm_loc, kSelBlock, 0, stream>>>(P);
-            if (!P.fused_select) {
-                gather_p2p_kernel<real><<<(unsigned)((Rs + 255) / 256), 256, 0, stream>>>(P);
-                svec_p2p_kernel<real><<<(unsigned)((std::max(Rs, ld) + 255) / 256), 256, 0, stream>>>(P);
-            }
+            gather_p2p_kernel<real><<<(unsigned)((Rs + 255) / 256), 256, 0, stream>>>(P);
+            svec_p2p_kernel<real><<<(unsigned)((std::max(Rs, ld) + 255) / 256), 256, 0, stream>>>(P);
             update_fn()<<<upd_grid, kSelBlock, 0, stream>>>(P);
             return B2S_OK;
         }
