@@ -284,6 +284,13 @@ def run_b2s(a):
                     "kernel_share_of_pivot": upd / tot,
                     "other_kernels_ms": {"ratio": float(np.mean(prof["ratio_ms"])), "gather": float(np.mean(prof["gather_ms"]))},
                     "whole_pivot_GBps": bytes_per_pivot * value / 1e9}
+    # kernels launched inside the timed region: per-pivot kernels, or one cooperative loop kernel per batch
+    # (the library's batch: ~3 ms of pivots, 4..256 -- b2s_solver.cu pick_batch)
+    if "persistent" in loop_mode:
+        batch = int(min(256.0, max(4.0, 3e-3 / max(12e-6, 2.0 * slab_bytes / 5.0e12))))
+        launches = a.steps * ((P + batch - 1) // batch + 1)
+    else:
+        launches = (3 if world == 1 else 4) * pivots
     stats = s.stats()
     rows_note = None
     if a.skip_zero_rows and stats.rows_total:
@@ -301,7 +308,7 @@ def run_b2s(a):
                        "parallelism": f"constraint slabs x{world}" if world > 1 else "single GPU",
                        "skip_zero_rows": bool(a.skip_zero_rows), "update_variant": a.update_variant,
                        "loop": loop_mode},
-            "clocks": clocks, "gpu_launches": pivots if "persistent" in loop_mode else (3 if world == 1 else 2) * pivots, "wall_s_timed_region": wall}
+            "clocks": clocks, "gpu_launches": launches, "wall_s_timed_region": wall}
     if rows_note is not None:
         line["config"]["rows_streamed_fraction"] = rows_note
     if roofline:
