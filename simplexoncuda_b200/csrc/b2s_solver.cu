@@ -96,6 +96,17 @@ static double now_s()
 
 enum Stage { kEmpty = 0, kLoaded, kBuilt, kPriced, kReady, kPhaseDone };
 
+// Scratch device allocation of the kernel-level hooks: released on every return path.
+template <typename X>
+struct DevBuf {
+    X* p = nullptr;
+    cudaError_t alloc(size_t count) { return cudaMalloc(&p, sizeof(X) * (count ? count : 1)); }
+    ~DevBuf() { cudaFree(p); }
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+};
+
 template <typename real>
 struct SolverImpl final : SolverBase {
     int dev = 0;
@@ -1114,34 +1125,30 @@ struct SolverImpl final : SolverBase {
     // ---- device-vector primitives of include/reduction.cuh --------------------------------------
     int run_tournament_device(const real* dvals /* cnt+1 entries, [0] unused */, long long cnt, double* value, unsigned* index)
     {
-        real* dv = nullptr;
-        int *di = nullptr, *dk = nullptr;
-        DevState* dst = nullptr;
-        CK(cudaMalloc(&dv, sizeof(real) * kMaxSlots));
-        CK(cudaMalloc(&di, sizeof(int) * kMaxSlots));
-        CK(cudaMalloc(&dk, sizeof(int) * kMaxSlots));
-        CK(cudaMalloc(&dst, sizeof(DevState)));
-        CK(cudaMemsetAsync(dst, 0, sizeof(DevState), stream));
+        DevBuf<real> dv;
+        DevBuf<int> di, dk;
+        DevBuf<DevState> dst;
+        CK(dv.alloc(kMaxSlots));
+        CK(di.alloc(kMaxSlots));
+        CK(dk.alloc(kMaxSlots));
+        CK(dst.alloc(1));
+        CK(cudaMemsetAsync(dst.p, 0, sizeof(DevState), stream));
         PivotParams<real> Q{};
         Q.cost = const_cast<real*>(dvals);
         Q.Rc = cnt + 1;
         Q.fold_from = LLONG_MAX;
-        Q.cslot_v = dv;
-        Q.cslot_i = di;
-        Q.cslot_k = dk;
-        Q.st = dst;
+        Q.cslot_v = dv.p;
+        Q.cslot_i = di.p;
+        Q.cslot_k = dk.p;
+        Q.st = dst.p;
         Q.rule = opt.pivot_rule;
         Q.Gc = (int)std::max<long long>(1, std::min<long long>((cnt + kSelBlock - 1) / kSelBlock, kMaxSlots));
         select_kernel<real><<<Q.Gc, kSelBlock, 0, stream>>>(Q);
         DevState hs;
-        CK(cudaMemcpyAsync(&hs, dst, sizeof(DevState), cudaMemcpyDeviceToHost, stream));
+        CK(cudaMemcpyAsync(&hs, dst.p, sizeof(DevState), cudaMemcpyDeviceToHost, stream));
         CK(cudaStreamSynchronize(stream));
         if (value) *value = hs.cq;
         if (index) *index = (unsigned)hs.q;
-        cudaFree(dv);
-        cudaFree(di);
-        cudaFree(dk);
-        cudaFree(dst);
         return B2S_OK;
     }
 
@@ -1150,12 +1157,10 @@ struct SolverImpl final : SolverBase {
         if (sizeof(real) != sizeof(double)) return fail(B2S_ERR_ARG, "fp64 only");
         if (cnt < 1 || !dvec) return fail(B2S_ERR_ARG, "minElement needs a non-empty device vector");
         CK(cudaSetDevice(dev));
-        real* tmp = nullptr;  // the reference reduces a scratch copy too (src/reduction.cu:87-89)
-        CK(cudaMalloc(&tmp, sizeof(real) * ((size_t)cnt + 1)));
-        CK(cudaMemcpyAsync(tmp + 1, dvec, sizeof(real) * (size_t)cnt, cudaMemcpyDeviceToDevice, stream));
-        int rc = run_tournament_device(tmp, cnt, value, index);
-        cudaFree(tmp);
-        return rc;
+        DevBuf<real> tmp;  // the reference reduces a scratch copy too (src/reduction.cu:87-89)
+        CK(tmp.alloc((size_t)cnt + 1));
+        CK(cudaMemcpyAsync(tmp.p + 1, dvec, sizeof(real) * (size_t)cnt, cudaMemcpyDeviceToDevice, stream));
+        return run_tournament_device(tmp.p, cnt, value, index);
     }
 
     int ratio_min_device(const double* known, const double* column, long long cnt, double* value, unsigned* index) override
@@ -1163,13 +1168,11 @@ struct SolverImpl final : SolverBase {
         if (sizeof(real) != sizeof(double)) return fail(B2S_ERR_ARG, "fp64 only");
         if (cnt < 1 || !known || !column) return fail(B2S_ERR_ARG, "ratio minElement needs two device vectors");
         CK(cudaSetDevice(dev));
-        real* tmp = nullptr;
-        CK(cudaMalloc(&tmp, sizeof(real) * ((size_t)cnt + 1)));
+        DevBuf<real> tmp;
+        CK(tmp.alloc((size_t)cnt + 1));
         ratio_vector_kernel<real><<<(unsigned)((cnt + 255) / 256), 256, 0, stream>>>(
-            reinterpret_cast<const real*>(known), reinterpret_cast<const real*>(column), cnt, tmp + 1);
-        int rc = run_tournament_device(tmp, cnt, value, index);
-        cudaFree(tmp);
-        return rc;
+            reinterpret_cast<const real*>(known), reinterpret_cast<const real*>(column), cnt, tmp.p + 1);
+        return run_tournament_device(tmp.p, cnt, value, index);
     }
 
     int max_le_zero_device(const double* dvec, long long cnt, int* result) override
@@ -1177,13 +1180,12 @@ struct SolverImpl final : SolverBase {
         if (sizeof(real) != sizeof(double)) return fail(B2S_ERR_ARG, "fp64 only");
         if (cnt < 1 || !dvec || !result) return fail(B2S_ERR_ARG, "isLessOrEqualThanZero needs a device vector");
         CK(cudaSetDevice(dev));
-        real* out = nullptr;
-        CK(cudaMalloc(&out, sizeof(real)));
-        max_vector_kernel<real><<<1, kSelBlock, 0, stream>>>(reinterpret_cast<const real*>(dvec), cnt, out);
+        DevBuf<real> out;
+        CK(out.alloc(1));
+        max_vector_kernel<real><<<1, kSelBlock, 0, stream>>>(reinterpret_cast<const real*>(dvec), cnt, out.p);
         real h = 0;
-        CK(cudaMemcpyAsync(&h, out, sizeof(real), cudaMemcpyDeviceToHost, stream));
+        CK(cudaMemcpyAsync(&h, out.p, sizeof(real), cudaMemcpyDeviceToHost, stream));
         CK(cudaStreamSynchronize(stream));
-        cudaFree(out);
         const double d = (double)h;  // compare(max) <= 0  <=>  max < 1e-9   (src/reduction.cu:200)
         *result = (fabs(d) < 1e-9 || d < 0.0) ? 1 : 0;
         return B2S_OK;
@@ -1197,39 +1199,13 @@ struct SolverImpl final : SolverBase {
         std::vector<real> h((size_t)cnt + 1);
         h[0] = 0;
         for (long long i = 0; i < cnt; ++i) h[(size_t)i + 1] = (real)vec[i];
-        real* dcost = nullptr;
-        real* dv = nullptr;
-        int *di = nullptr, *dk = nullptr;
-        DevState* dst = nullptr;
-        CK(cudaMalloc(&dcost, sizeof(real) * ((size_t)cnt + 1)));
-        CK(cudaMalloc(&dv, sizeof(real) * kMaxSlots));
-        CK(cudaMalloc(&di, sizeof(int) * kMaxSlots));
-        CK(cudaMalloc(&dk, sizeof(int) * kMaxSlots));
-        CK(cudaMalloc(&dst, sizeof(DevState)));
-        CK(cudaMemsetAsync(dst, 0, sizeof(DevState), stream));
-        CK(cudaMemcpyAsync(dcost, h.data(), sizeof(real) * ((size_t)cnt + 1), cudaMemcpyHostToDevice, stream));
-        PivotParams<real> Q{};
-        Q.cost = dcost;
-        Q.Rc = cnt + 1;
-        Q.fold_from = LLONG_MAX;
-        Q.cslot_v = dv;
-        Q.cslot_i = di;
-        Q.cslot_k = dk;
-        Q.st = dst;
-        Q.rule = opt.pivot_rule;
-        Q.Gc = (int)std::max<long long>(1, std::min<long long>((cnt + kSelBlock - 1) / kSelBlock, kMaxSlots));
-        select_kernel<real><<<Q.Gc, kSelBlock, 0, stream>>>(Q);
-        DevState hs;
-        CK(cudaMemcpyAsync(&hs, dst, sizeof(DevState), cudaMemcpyDeviceToHost, stream));
-        CK(cudaStreamSynchronize(stream));
-        if (value) *value = hs.cq;
-        if (index) *index = hs.q;
-        cudaFree(dcost);
-        cudaFree(dv);
-        cudaFree(di);
-        cudaFree(dk);
-        cudaFree(dst);
-        return B2S_OK;
+        DevBuf<real> dcost;
+        CK(dcost.alloc((size_t)cnt + 1));
+        CK(cudaMemcpyAsync(dcost.p, h.data(), sizeof(real) * ((size_t)cnt + 1), cudaMemcpyHostToDevice, stream));
+        unsigned idx = 0;
+        int rc = run_tournament_device(dcost.p, cnt, value, &idx);
+        if (index) *index = (int)idx;
+        return rc;
     }
 
     int bench_update(int launches, int flush, float* ms, double* bytes) override
