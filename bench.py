@@ -190,7 +190,11 @@ def run_reference(a):
         line.update(value=value, ms_per_step=1e3 * a.pivots_per_step / value, clocks=clocks, gpu_launches=0,
                     cpu_baseline={"value": value, "unit": UNIT, "cores": 1, "kind": "reference", "sample": sample,
                                   "device": "NVIDIA B200 (the reference has no CPU path; its host loop is one thread)"},
-                    e2e={"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
+                    e2e={"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                    per_phase={"phase1_pivots_per_s": res["pivots_phase1"] / max(res["seconds_loop_phase1"], 1e-9),
+                               "phase2_pivots_per_s": res["pivots_phase2"] / max(res["seconds_loop_phase2"], 1e-9),
+                               "phase1_tableau_rows": 1 + a.vars + 2 * a.constraints,
+                               "phase2_tableau_rows": 1 + a.vars + a.constraints})
     else:
         cb = cpu_baseline(a)
         cb["sample"] += "; oracle/_ref absent, so the oracle port stands in for the reference"
@@ -342,7 +346,10 @@ def run_b2s(a):
                        "d2h_bytes_per_step": int(n * 8 + 8 + m * 4) * world,
                        "step": f"one complete two-phase solve from pinned host arrays: status {r['status']}, "
                                f"{r['stats'].pivots_phase1}+{r['stats'].pivots_phase2} pivots in {secs:.3f} s "
-                               f"(max over ranks; load {r['stats'].seconds_load:.3f} s)", "objective": r["objective"]}
+                               f"(max over ranks; load {r['stats'].seconds_load:.3f} s)", "objective": r["objective"],
+                       "per_phase": {"phase1_pivots_per_s": r["stats"].pivots_phase1 / max(r["stats"].seconds_phase1, 1e-9),
+                                     "phase2_pivots_per_s": r["stats"].pivots_phase2 / max(r["stats"].seconds_phase2, 1e-9),
+                                     "tableau_rows_streamed_both_phases": dims["rows_stored"]}}
     elif not a.no_e2e:
         line["e2e"] = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                        "step": "skipped: the constraint matrix of this configuration does not fit in host memory; "
