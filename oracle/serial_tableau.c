@@ -7,7 +7,8 @@
  * (simplexoncuda_b200/csrc) never links or calls it.
  *
  * Parity status: PINNED.  The restatement reproduces the reference's published per-phase
- * pivot counts (data/measures/<gpu>/benchmark_<n>_<m>.txt, lines-1 per phase) when the three
+ * pivot counts (data/measures/<gpu>/benchmark_<n>_<m>.txt, lines-1 per phase) on ALL 36 published
+ * instances plus the false-INFEASIBLE 37th (tests/golden/oracle_results.json) when the three
  * kernel seeds are derived with MSVC rand() -- see tests/test_oracle_golden.py -- and it is
  * cross-checked on the GPU box against the unmodified reference build in oracle/_ref
  * (tests/test_reference_parity.py).

@@ -210,6 +210,8 @@ def test_false_infeasible_golden(S):
         s.generate(1024, 8192, S.seed_triplet(110592, S.RAND_MSVC), 1, 100)
         r = s.solve()
     assert r["status"] == S.INFEASIBLE and r["stats"].pivots_phase1 == 14063
+    fx = ORC["1024_8192_110592"]   # the serial oracle ends the same way: cost[0] = -1.9e-9 <= -1e-9
+    assert fx["status"] == -1 and str(r["stats"].trace_hash) == fx["trace_hash"]
 
 
 # ---- size-independent properties at full size ------------------------------------------------------

@@ -129,7 +129,7 @@ def test_oracle_fixture_agrees_with_published_counts():
             if inst["phase2_ran"]:
                 assert ORC[key]["pivots_phase2"] == inst["pivots_phase2"], key
             checked += 1
-    assert checked >= 30
+    assert checked >= 37   # all 36 published instances + the MX250 run of 1024x8192 with the un-bumped seed
 
 
 def test_stepping_equals_whole_solve():
