@@ -8,6 +8,7 @@
 #include "b2s_kernels.cuh"
 #include "b2s_p2p.cuh"
 #include "b2s_persistent.cuh"
+#include "b2s_bulk.cuh"
 
 #include <algorithm>
 #include <chrono>
@@ -140,6 +141,7 @@ struct SolverImpl final : SolverBase {
 
     PivotParams<real> P{};
     int upd_grid = 0;
+    size_t upd_smem = 0;  // dynamic shared memory of the update kernel (bulk-copy variant only)
     int loop_grid = 0;  // persistent loop kernel: co-resident CTAs
     cudaGraphExec_t graph_exec = nullptr;
     int graph_batch = 0;
@@ -387,12 +389,12 @@ struct SolverImpl final : SolverBase {
     struct Variant {
         int vb, u, hint, dyn;
     };
-    static constexpr int kNumVariants = 14;
+    static constexpr int kNumVariants = 15;  // 14 = bulk-copy (TMA engine) pipeline, b2s_bulk.cuh
     Variant variant() const
     {
         static const Variant table[kNumVariants] = {{16, 8, 0, 0}, {16, 8, 1, 0}, {32, 4, 0, 0}, {32, 4, 1, 0}, {32, 8, 0, 0},
                                                     {16, 4, 0, 0}, {16, 8, 2, 0}, {32, 8, 1, 0}, {32, 8, 0, 1}, {32, 4, 0, 1},
-                                                    {16, 4, 0, 1}, {32, 8, 1, 1}, {32, 8, 2, 1}, {16, 8, 0, 1}};
+                                                    {16, 4, 0, 1}, {32, 8, 1, 1}, {32, 8, 2, 1}, {16, 8, 0, 1}, {32, 8, 0, 1}};
         int v = opt.update_variant;
         if (v < 0 || v >= kNumVariants) v = 8;
         if (use_persistent()) v = 8;  // the loop kernel is built for the 256-bit / 8-row / ticketed geometry
@@ -440,6 +442,7 @@ struct SolverImpl final : SolverBase {
             case 11: return pick_skip<32, 8, 1, true>();
             case 12: return pick_skip<32, 8, 2, true>();
             case 13: return pick_skip<16, 8, 0, true>();
+            case 14: return opt.skip_zero_rows ? pick_skip<32, 8, 0, true>() : (UpdateFn)update_bulk_kernel<real>;
         }
     }
 
@@ -506,6 +509,12 @@ struct SolverImpl final : SolverBase {
         P.ntiles = ((Rs + rows_tile - 1) / rows_tile) * P.nchunks;
         upd_grid = (int)std::max<long long>(std::min<long long>(grid, P.ntiles), std::min(P.Gc, grid));
         upd_grid = std::max(upd_grid, 1);
+        upd_smem = 0;
+        if (update_fn() == (UpdateFn)update_bulk_kernel<real>) {
+            upd_smem = (size_t)kBulkStages * kBulkRows * kBulkCols * 8;
+            cudaFuncSetAttribute(update_bulk_kernel<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)upd_smem);
+            upd_grid = num_sms;
+        }
         if (opt.persistent) {
             int occ_l = 0;
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_l, loop_fn(), kSelBlock, 0);
@@ -701,7 +710,7 @@ struct SolverImpl final : SolverBase {
             ratio_p2p_kernel<real><<<P.Gm_loc, kSelBlock, 0, stream>>>(P);
             gather_p2p_kernel<real><<<(unsigned)((Rs + 255) / 256), 256, 0, stream>>>(P);
             svec_p2p_kernel<real><<<(unsigned)((std::max(Rs, ld) + 255) / 256), 256, 0, stream>>>(P);
-            update_fn()<<<upd_grid, kSelBlock, 0, stream>>>(P);
+            update_fn()<<<upd_grid, kSelBlock, upd_smem, stream>>>(P);
             return B2S_OK;
         }
 #ifdef B2S_WITH_NCCL
@@ -718,7 +727,7 @@ struct SolverImpl final : SolverBase {
         }
         ratio_kernel<real, false><<<P.Gm, kSelBlock, 0, stream>>>(P);
         gather_kernel<real, false><<<(unsigned)((work + 255) / 256), 256, 0, stream>>>(P);
-        update_fn()<<<upd_grid, kSelBlock, 0, stream>>>(P);
+        update_fn()<<<upd_grid, kSelBlock, upd_smem, stream>>>(P);
         return B2S_OK;
     }
 
@@ -761,7 +770,7 @@ struct SolverImpl final : SolverBase {
         gather_kernel<real, true><<<(unsigned)((Rs + 255) / 256), 256, 0, stream>>>(P);
         NK(ncclAllReduce(rowp, rowp, (size_t)Rs, sizeof(real) == 8 ? ncclUint64 : ncclUint32, ncclSum, comm, stream));
         svec_kernel<real><<<(unsigned)((ld + 255) / 256), 256, 0, stream>>>(P);
-        update_fn()<<<upd_grid, kSelBlock, 0, stream>>>(P);
+        update_fn()<<<upd_grid, kSelBlock, upd_smem, stream>>>(P);
         return B2S_OK;
     }
 #endif
@@ -1223,7 +1232,7 @@ struct SolverImpl final : SolverBase {
         for (int k = 0; k < launches; ++k) {
             if (flush) CK(cudaMemsetAsync(flush_buf, k & 0xff, flush_bytes, stream));
             CK(cudaEventRecord(ev[2 * k], stream));
-            update_fn()<<<upd_grid, kSelBlock, 0, stream>>>(P);
+            update_fn()<<<upd_grid, kSelBlock, upd_smem, stream>>>(P);
             CK(cudaEventRecord(ev[2 * k + 1], stream));
         }
         CK(cudaGetLastError());
@@ -1257,7 +1266,7 @@ struct SolverImpl final : SolverBase {
             CK(cudaEventRecord(ev[4 * k + 1], stream));
             gather_kernel<real, false><<<(unsigned)((work + 255) / 256), 256, 0, stream>>>(P);
             CK(cudaEventRecord(ev[4 * k + 2], stream));
-            update_fn()<<<upd_grid, kSelBlock, 0, stream>>>(P);
+            update_fn()<<<upd_grid, kSelBlock, upd_smem, stream>>>(P);
             CK(cudaEventRecord(ev[4 * k + 3], stream));
         }
         CK(cudaGetLastError());

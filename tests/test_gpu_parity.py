@@ -169,7 +169,8 @@ def test_blands_rule_breaks_cycling(S):
                                   dict(batch=1), dict(update_variant=7, skip_zero_rows=True), dict(update_variant=4),
                                   dict(update_variant=10), dict(update_variant=9, skip_zero_rows=True), dict(update_variant=0),
                                   dict(persistent=False), dict(persistent=False, use_graph=False),
-                                  dict(persistent=False, skip_zero_rows=True), dict(persistent=True, batch=3)])
+                                  dict(persistent=False, skip_zero_rows=True), dict(persistent=True, batch=3),
+                                  dict(persistent=False, update_variant=14), dict(persistent=False, update_variant=14, fold_artificials=False)])
 def test_options_do_not_change_results(S, opts):
     A, b, c = O.generate(300, 260, O.seed_triplet(77, 1), 1, 100)
     check_solve(S, A, b, c, **opts)

@@ -13,16 +13,16 @@ import simplexoncuda_b200 as S
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
 m = int(sys.argv[2]) if len(sys.argv) > 2 else 8192
 launches = int(sys.argv[3]) if len(sys.argv) > 3 else 30
-variants = [int(v) for v in sys.argv[4].split(",")] if len(sys.argv) > 4 else list(range(14))
+variants = [int(v) for v in sys.argv[4].split(",")] if len(sys.argv) > 4 else list(range(15))
 tgs = sys.argv[5].split(",") if len(sys.argv) > 5 else [""]
 names = {0: "v16 u8", 1: "v16 u8 .cs", 2: "v32 u4", 3: "v32 u4 .cs", 4: "v32 u8", 5: "v16 u4", 6: "v16 u8 noalloc",
          7: "v32 u8 .cs", 8: "v32 u8 dyn", 9: "v32 u4 dyn", 10: "v16 u4 dyn", 11: "v32 u8 .cs dyn", 12: "v32 u8 noalloc dyn",
-         13: "v16 u8 dyn"}
+         13: "v16 u8 dyn", 14: "bulk-copy (TMA) ring"}
 for tg in tgs:
     if tg:
         os.environ["B2S_TILE_GROUPS"] = tg
     for var in variants:
-        with S.Solver(update_variant=var) as s:
+        with S.Solver(update_variant=var, persistent=False) as s:
             s.generate(n, m, (1, 2, 3), 1, 100)
             ms, nbytes = s.bench_update(launches, flush_l2=False)
         ms = ms[3:]
