@@ -256,6 +256,7 @@ struct PivotParams {
     long long arena_rows;          // capacity of one arena rowp buffer (elements)
     unsigned char* peers[kMaxPeers];
     // update-kernel tiling
+    int serpentine; // alternate the sweep direction of the update every pivot (L2 reuse across pivots)
     int log2_tpr;   // log2(threads per tableau row)
     int nchunks;    // column chunks per row
     int tile_groups;  // unrolled row groups per tile

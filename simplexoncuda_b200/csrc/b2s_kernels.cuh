@@ -376,7 +376,8 @@ __global__ void __launch_bounds__(256) svec_kernel(PivotParams<real> P)
 // ---------------------------------------------------------------------------------------------
 template <typename real, int VB, int U, int HINT, bool SKIP, bool DYN, bool COH>
 __device__ __forceinline__ void stream_tiles(const PivotParams<real>& P, const real* rowp, const real* svec,
-                                             const real* colv, real piv, long long lp, long long* s_next)
+                                             const real* colv, real piv, long long lp, long long* s_next,
+                                             bool reverse = false)
 {
     constexpr int EPT = VB / (int)sizeof(real);
     const int tx = threadIdx.x & ((1 << P.log2_tpr) - 1);
@@ -393,8 +394,13 @@ __device__ __forceinline__ void stream_tiles(const PivotParams<real>& P, const r
     while (tile < P.ntiles) {
         if (DYN && threadIdx.x == 0)
             *s_next = (long long)atomicAdd(&P.st->tile_ticket, 1u) + gridDim.x;
-        const int chunk = (int)(tile % P.nchunks);
-        const long long rb = tile / P.nchunks;
+        // Serpentine sweep: odd pivots walk the tableau backwards, so the tiles the previous pivot touched last
+        // -- still sitting (dirty) in the 126 MB L2 -- are the first ones this pivot reads and rewrites, and
+        // never travel to HBM in between.  (Explicit L2 evict_first / evict_last hints on top of this were
+        // measured and changed nothing: profiles/r01_scaling_and_loop_modes.md.)
+        const long long tmap = reverse ? (P.ntiles - 1 - tile) : tile;
+        const int chunk = (int)(tmap % P.nchunks);
+        const long long rb = tmap / P.nchunks;
         const long long c = chunk * chunk_cols + (long long)tx * EPT;
         if (c < P.ld) {
             const long long r0 = rb * tile_rows + ty;
@@ -466,7 +472,8 @@ __global__ void __launch_bounds__(kSelBlock, (VB * U <= 128) ? 2 : 1) update_ker
     const real* rowp = P.rowp;
     if (blockIdx.x < P.Gc) cost_select_blocks<real, true>(P, rowp, (real)__ldcg(&P.st->sc), sm, &s_flag);
 
-    stream_tiles<real, VB, U, HINT, SKIP, DYN, false>(P, rowp, P.s, nullptr, (real)0, -1, &s_next);
+    const bool reverse = P.serpentine && (__ldcg(&P.st->pivots) & 1);
+    stream_tiles<real, VB, U, HINT, SKIP, DYN, false>(P, rowp, P.s, nullptr, (real)0, -1, &s_next, reverse);
     if (DYN) {
         // the last CTA to leave re-arms the ticket counters for the next launch
         if (threadIdx.x == 0) {
@@ -620,6 +627,9 @@ __global__ void __launch_bounds__(256) bench_fill_kernel(PivotParams<real> P)
         P.st->status = kRunning;
     }
 }
+
+// b2s_bench_update: advance the pivot counter between launches so the sweep direction alternates as in a solve
+__global__ void bench_bump_kernel(DevState* st) { st->pivots += 1; }
 
 // Stand-alone vector primitives behind the reference's reduction.cuh entry points.
 template <typename real>

@@ -60,9 +60,9 @@ __device__ __forceinline__ bool grid_barrier(unsigned* counter, unsigned& epoch,
 // Phase D's streaming loop is kept out of line so that it gets the same register allocation as the
 // stand-alone update_kernel (8 x 256-bit loads in flight need 64 data registers of the 128 available).
 template <typename real, int VB, int U, bool SKIP>
-__device__ __noinline__ void stream_phase(const PivotParams<real>& P, const real* rowp, long long* s_next)
+__device__ __noinline__ void stream_phase(const PivotParams<real>& P, const real* rowp, long long* s_next, bool reverse)
 {
-    stream_tiles<real, VB, U, 3, SKIP, true, true>(P, rowp, P.s, nullptr, (real)0, -1, s_next);
+    stream_tiles<real, VB, U, 3, SKIP, true, true>(P, rowp, P.s, nullptr, (real)0, -1, s_next, reverse);
 }
 
 template <typename real, int VB, int U, bool SKIP>
@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(kSelBlock, 1) pivot_loop_kernel(const __grid_c
 
         // ---- phase D: cost update + next entering tournament, then the rank-1 update ----------------
         if (blockIdx.x < P.Gc) cost_select_blocks<real, true, true>(P, rowp, sc, sm, &s_flag);
-        stream_phase<real, VB, U, SKIP>(P, rowp, &s_next);
+        stream_phase<real, VB, U, SKIP>(P, rowp, &s_next, P.serpentine && (seq & 1ull));
         if (!grid_barrier(&st->bar_count, epoch, &s_ok)) break;
     }
 }

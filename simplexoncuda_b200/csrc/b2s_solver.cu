@@ -478,6 +478,8 @@ struct SolverImpl final : SolverBase {
         P.Gm_loc0 = col0 / kSelBlock;
         P.Gm_loc = world > 1 ? m_loc / kSelBlock : P.Gm;
         P.Gc = (int)std::max<long long>(1, std::min<long long>((Rc - 1 + kSelBlock - 1) / kSelBlock, kMaxSlots));
+        P.serpentine = 1;
+        if (const char* e = getenv("B2S_SERPENTINE")) P.serpentine = atoi(e) != 0;
         P.rank = rank;
         P.world = world;
         P.arena_rows = arena_rows;
@@ -1231,6 +1233,7 @@ struct SolverImpl final : SolverBase {
         for (auto& e : ev) CK(cudaEventCreate(&e));
         for (int k = 0; k < launches; ++k) {
             if (flush) CK(cudaMemsetAsync(flush_buf, k & 0xff, flush_bytes, stream));
+            bench_bump_kernel<<<1, 1, 0, stream>>>(st);
             CK(cudaEventRecord(ev[2 * k], stream));
             update_fn()<<<upd_grid, kSelBlock, upd_smem, stream>>>(P);
             CK(cudaEventRecord(ev[2 * k + 1], stream));
