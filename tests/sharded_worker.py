@@ -23,7 +23,13 @@ def main():
     sharding.init_sharded_solver(s, dist)
     for cs in cases:
         seeds = S.seed_triplet(cs["seed"], cs["flavour"])
-        s.generate(cs["n"], cs["m"], seeds, cs["lo"], cs["hi"])
+        if cs.get("load") == "host":   # the twoPhaseMethod path: every rank loads its slab from the host arrays
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import oracle_py as O      # instance generation only (test infrastructure)
+            A, b, c = O.generate(cs["n"], cs["m"], seeds, cs["lo"], cs["hi"])
+            s.load(A, b, c)
+        else:
+            s.generate(cs["n"], cs["m"], seeds, cs["lo"], cs["hi"])
         r = s.solve()
         out = {"case": cs, "status": r["status"], "pivots": [r["stats"].pivots_phase1, r["stats"].pivots_phase2],
                "hash": str(r["stats"].trace_hash), "objective": r["objective"], "basis": r["basis"].tolist(),

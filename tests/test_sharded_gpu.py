@@ -30,7 +30,8 @@ def test_sharded_solves_match_oracle(world):
         pytest.skip(f"needs {world} GPUs")
     cases = [dict(n=300, m=1024 * world // 2, seed=11, flavour=1, lo=1, hi=100),
              dict(n=64, m=512 * world, seed=5, flavour=0, lo=-100, hi=100),
-             dict(n=1024, m=1024 * world // 2, seed=103424, flavour=1, lo=1, hi=100)]
+             dict(n=1024, m=1024 * world // 2, seed=103424, flavour=1, lo=1, hi=100),
+             dict(n=200, m=512 * world, seed=9, flavour=0, lo=1, hi=100, load="host")]
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", "29713", os.path.join(ROOT, "tests", "sharded_worker.py"),
            json.dumps(cases)]
