@@ -554,25 +554,7 @@ struct SolverImpl final : SolverBase {
         int rc = prepare(n_, m_);
         if (rc) return rc;
         if ((rc = zero_fill_for_load())) return rc;
-        if (world > 1 && (double)n * (double)m * sizeof(double) <= 2e9) {
-            // sharded: a strided host copy of one slab degenerates into n small DMA rows (0.3-1 s at 8192x8192);
-            // one contiguous copy of A into a staging buffer (20 ms from pinned memory) and a device-side
-            // slab extraction is an order of magnitude faster
-            if ((rc = ensure_stage((size_t)n * (size_t)m))) return rc;
-            CK(cudaMemcpyAsync(stage_dev, A, sizeof(double) * (size_t)n * (size_t)m, cudaMemcpyHostToDevice, stream));
-            convert_rows<<<num_sms * 8, 256, 0, stream>>>(T + ld, ld, stage_dev + col0, (long long)m, (long long)n, m_loc);
-            if (sizeof(real) == sizeof(double)) {
-                CK(cudaMemcpyAsync(T, b + col0, sizeof(double) * m_loc, cudaMemcpyHostToDevice, stream));
-                CK(cudaMemcpyAsync(c_dev, c, sizeof(double) * n, cudaMemcpyHostToDevice, stream));
-            } else {
-                std::vector<real> bb((size_t)m_loc), cc((size_t)n);
-                for (int i = 0; i < m_loc; ++i) bb[(size_t)i] = (real)b[col0 + i];
-                for (int j = 0; j < n; ++j) cc[(size_t)j] = (real)c[j];
-                CK(cudaMemcpyAsync(T, bb.data(), sizeof(real) * m_loc, cudaMemcpyHostToDevice, stream));
-                CK(cudaMemcpyAsync(c_dev, cc.data(), sizeof(real) * n, cudaMemcpyHostToDevice, stream));
-                CK(cudaStreamSynchronize(stream));
-            }
-        } else if (sizeof(real) == sizeof(double)) {
+        if (sizeof(real) == sizeof(double)) {
             // rows 1..n <- A (variable-major, row pitch m), local slab columns only; row 0 <- b
             CK(cudaMemcpy2DAsync(T + ld, sizeof(real) * ld, A + col0, sizeof(double) * m, sizeof(double) * m_loc,
                                  (size_t)n, cudaMemcpyHostToDevice, stream));
