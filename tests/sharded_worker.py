@@ -19,7 +19,8 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     cases = json.loads(sys.argv[1])
-    s = S.Solver(device=local)
+    # B2S_TEST_PERSISTENT=1 forces the persistent loop kernel (with peer-memory exchanges) on the sharded solve
+    s = S.Solver(device=local, persistent=True if os.environ.get("B2S_TEST_PERSISTENT") == "1" else "auto")
     sharding.init_sharded_solver(s, dist)
     for cs in cases:
         seeds = S.seed_triplet(cs["seed"], cs["flavour"])

@@ -24,10 +24,20 @@ def _ngpus():
         return 0
 
 
+@pytest.mark.parametrize("mode", ["p2p-launches", "p2p-persistent", "nccl"])
 @pytest.mark.parametrize("world", [2, 4, 8])
-def test_sharded_solves_match_oracle(world):
+def test_sharded_solves_match_oracle(world, mode):
+    """All three exchange implementations: peer-memory kernels (default), the persistent loop kernel with
+    peer-memory exchanges, and the NCCL fallback (B2S_P2P=0)."""
     if _ngpus() < world:
         pytest.skip(f"needs {world} GPUs")
+    if mode != "p2p-launches" and world > 2:
+        pytest.skip("alternative exchange paths are exercised at world size 2")
+    env = dict(os.environ)
+    if mode == "p2p-persistent":
+        env["B2S_TEST_PERSISTENT"] = "1"
+    if mode == "nccl":
+        env["B2S_P2P"] = "0"
     cases = [dict(n=300, m=1024 * world // 2, seed=11, flavour=1, lo=1, hi=100),
              dict(n=64, m=512 * world, seed=5, flavour=0, lo=-100, hi=100),
              dict(n=1024, m=1024 * world // 2, seed=103424, flavour=1, lo=1, hi=100),
@@ -35,7 +45,7 @@ def test_sharded_solves_match_oracle(world):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", "29713", os.path.join(ROOT, "tests", "sharded_worker.py"),
            json.dumps(cases)]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=1200)
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=1200, env=env)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     results = [json.loads(l[len("RESULT "):]) for l in out.stdout.splitlines() if l.startswith("RESULT ")]
     assert len(results) == len(cases)
