@@ -21,6 +21,8 @@
 #ifndef B2S_H
 #define B2S_H
 
+#include <stddef.h> /* size_t */
+
 #ifdef __cplusplus
 extern "C" {
 #endif

@@ -32,4 +32,8 @@ FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -fmad=fa
 # C++ client of the tabular_t-level drop-in API (used by tests/test_tabular_level.py on the GPU box)
 "$NVCC" -gencode arch=compute_100a,code=sm_100a -O2 -std=c++17 -I"$HERE/../../include/compat" \
     -o "$OUT/test_tabular_level" "$HERE/../../tests/cpp/tabular_level.cu" -L"$OUT" -lb2s_compat -lb2s -Xlinker -rpath,'$ORIGIN'
-echo "built $OUT/libb2s.so $OUT/libb2s_compat.so $OUT/test_tabular_level"
+# plain C99 client of the C ABI (proves the header is C, used by tests/test_tabular_level.py)
+GCC=/usr/bin/gcc; [ -x "$GCC" ] || GCC=gcc
+"$GCC" -std=c99 -pedantic -Wall -Wextra -I"$HERE/../../include" "$HERE/../../examples/solve_file.c" \
+    -L"$OUT" -lb2s -Wl,-rpath,'$ORIGIN' -o "$OUT/example_solve_file"
+echo "built $OUT/libb2s.so $OUT/libb2s_compat.so $OUT/test_tabular_level $OUT/example_solve_file"

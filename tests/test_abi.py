@@ -67,3 +67,14 @@ def test_text_problem_reader():
     assert (p.vars, p.constraints) == (3, 2)
     assert p.constraintsMatrix.tolist() == [[1.0, 1.0], [3.0, 5.0], [2.0, 1.0]]  # variable-major
     assert p.knownTermsVector.tolist() == [10.0, 8.0] and p.objectiveFunction.tolist() == [8.0, 10.0, 7.0]
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/b2s.h must be consumable from C (the drop-in boundary is a C ABI): compile it alone as C99."""
+    import subprocess
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "b2s.h"\nint main(void) { b2s_options o; (void)o; return (int)sizeof(b2s_stats) == 0; }\n')
+    gcc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    out = subprocess.run([gcc, "-std=c99", "-pedantic", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"),
+                          str(src)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr

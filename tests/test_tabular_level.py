@@ -50,3 +50,18 @@ def test_tabular_level_client(tmp_path, n, m, seed, lo):
     st = o.iterate(-1)
     assert res["status"] == st
     assert res["cost0"] == o.costs()[0] and res["base"] == o.basis().tolist()
+
+
+C_CLIENT = os.path.join(ROOT, "simplexoncuda_b200", "lib", "example_solve_file")
+
+
+@pytest.mark.skipif(not os.path.exists(C_CLIENT), reason="C client not built")
+def test_plain_c_client(tmp_path):
+    """examples/solve_file.c (C99, gcc) through the C ABI on the reference's smallProblem: optimum 64 at x=(8,0,0)."""
+    lp = tmp_path / "small.txt"
+    lp.write_text("3 2\n8 10 7\n1 3 2 10\n1 5 1 8\n")
+    out = subprocess.run([C_CLIENT, str(lp)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    lines = out.stdout.strip().splitlines()
+    assert lines[0].startswith("status 0  pivots 2+2")
+    assert lines[1] == "optimal value 64" and lines[2] == "x = 8 0 0" and lines[3] == "basis = 3 0"
