@@ -461,7 +461,6 @@ __device__ __forceinline__ void stream_tiles(const PivotParams<real>& P, const r
 template <typename real, int VB, int U, int HINT, bool SKIP, bool DYN>
 __global__ void __launch_bounds__(kSelBlock, (VB * U <= 128) ? 2 : 1) update_kernel(PivotParams<real> P)
 {
-    constexpr int EPT = VB / (int)sizeof(real);
     __shared__ TreeSmem<real> sm;
     __shared__ int s_flag;
     __shared__ long long s_next;
