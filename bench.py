@@ -241,7 +241,7 @@ def run_b2s(a):
     dims = s.dims()
     elem = 8
     slab_bytes = dims["rows_stored"] * (m // world) * elem
-    persistent_on = a.loop == "persistent" or (a.loop == "auto" and world == 1 and slab_bytes < 192e6)
+    persistent_on = a.loop == "persistent" or (a.loop == "auto" and world == 1 and slab_bytes < 32e6)
     loop_mode = ("persistent cooperative loop kernel (1 launch per batch of pivots)" if persistent_on
                  else "3 launches per pivot replayed as a CUDA graph")
     bytes_per_pivot = 2.0 * dims["rows_stored"] * (m // world) * elem  # per rank: read + write of the stored slab

@@ -70,7 +70,7 @@ typedef struct b2s_options {
                              device-wide ticket scheduler over 8-row tiles); others exist for tuning  */
     int persistent;       /* 1: run each batch of pivots as ONE persistent cooperative kernel with device-wide
                              barriers between the phases; 0: three launches per pivot (CUDA graph);
-                             2 (default): the loop kernel for L2-sized or sharded tableaux, launches otherwise */
+                             2 (default): the loop kernel for tableaux below 32 MB on one GPU, launches otherwise */
     int reserved[6];
 } b2s_options;
 

@@ -400,15 +400,16 @@ struct SolverImpl final : SolverBase {
         if (use_persistent()) v = 8;  // the loop kernel is built for the 256-bit / 8-row / ticketed geometry
         return table[v];
     }
-    // persistent: 0 = three launches per pivot, 1 = loop kernel, 2 = auto.  Measured on B200 (profiles/
-    // r01_loop_modes.md): the loop kernel wins whenever the fixed cost of a pivot matters (L2-resident
-    // tableaux or slabs: 46k vs 30k pivots/s at 1024x1024) and loses 2-8 % when a pivot streams hundreds of
-    // megabytes per GPU (8192x8192 on 1 or 2 GPUs), where graph-replayed launches are already hidden.
+    // persistent: 0 = three launches per pivot, 1 = loop kernel, 2 = auto.  Measured on B200 on complete solves
+    // (profiles/r01_scaling_and_loop_modes.md): the loop kernel wins for small tableaux (47.6k vs 43.2k pivots/s
+    // at 16 MB) and loses from ~30 MB upwards (37.6k vs 40.4k at 50 MB, 22.9k vs 27.6k at 100 MB, -2 % at 1 GB),
+    // where launches replayed from a CUDA graph cost about as much as grid barriers and the stand-alone update
+    // kernel streams a little faster than the loop kernel's phase D.
     bool use_persistent() const
     {
         if (opt.persistent == 0 || (world > 1 && !p2p)) return false;
         if (opt.persistent == 1) return true;
-        return world == 1 && (double)Rs * (double)ld * sizeof(real) < 192e6;
+        return world == 1 && (double)Rs * (double)ld * sizeof(real) < 32e6;
     }
     typedef void (*LoopFn)(PivotParams<real>, int);
     LoopFn loop_fn() const
