@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <chrono>
 #include <climits>
+#include <map>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -143,8 +144,7 @@ struct SolverImpl final : SolverBase {
     int upd_grid = 0;
     size_t upd_smem = 0;  // dynamic shared memory of the update kernel (bulk-copy variant only)
     int loop_grid = 0;  // persistent loop kernel: co-resident CTAs
-    cudaGraphExec_t graph_exec = nullptr;
-    int graph_batch = 0;
+    std::map<int, cudaGraphExec_t> graphs;  // captured batches of pivots, keyed by batch length
     long long pivots_p1 = 0, pivots_p2 = 0;
     double sec_load = 0, sec_p1 = 0, sec_p2 = 0;
 
@@ -165,8 +165,7 @@ struct SolverImpl final : SolverBase {
     void release()
     {
         cudaSetDevice(dev);
-        if (graph_exec) cudaGraphExecDestroy(graph_exec);
-        graph_exec = nullptr;
+        invalidate_graph();
         free_problem();
         cudaFree(st);
         cudaFreeHost(st_host);
@@ -373,9 +372,8 @@ struct SolverImpl final : SolverBase {
 
     void invalidate_graph()
     {
-        if (graph_exec) cudaGraphExecDestroy(graph_exec);
-        graph_exec = nullptr;
-        graph_batch = 0;
+        for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
+        graphs.clear();
     }
 
     static int ceil_log2(long long v)
@@ -814,18 +812,19 @@ struct SolverImpl final : SolverBase {
             CK(cudaGetLastError());
             return B2S_OK;
         }
-        if (!graph_exec || graph_batch != batch) {
-            invalidate_graph();
+        auto it = graphs.find(batch);
+        if (it == graphs.end()) {
             cudaGraph_t graph = nullptr;
+            cudaGraphExec_t exec = nullptr;
             CK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
             for (int k = 0; k < batch; ++k) enqueue_pivot();
             CK(cudaStreamEndCapture(stream, &graph));
-            cudaError_t e = cudaGraphInstantiate(&graph_exec, graph, 0);
+            cudaError_t e = cudaGraphInstantiate(&exec, graph, 0);
             cudaGraphDestroy(graph);
             if (e != cudaSuccess) return fail(B2S_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
-            graph_batch = batch;
+            it = graphs.emplace(batch, exec).first;
         }
-        CK(cudaGraphLaunch(graph_exec, stream));
+        CK(cudaGraphLaunch(it->second, stream));
         return B2S_OK;
     }
 
@@ -860,7 +859,16 @@ struct SolverImpl final : SolverBase {
         auto enqueue = [&](int slot) -> int {
             long long left = limit - start - enq;
             int batch = full;
-            if (!graphable && left < batch) batch = (int)std::max<long long>(left, 1);
+            if (left < batch) {
+                // a short budget: do not replay a full batch of mostly idle iterations.  Graphs exist per
+                // power-of-two length, so at most log2(full) extra captures ever happen per phase.
+                batch = (int)std::max<long long>(left, 1);
+                if (graphable) {
+                    int p2 = 1;
+                    while (p2 < batch) p2 <<= 1;
+                    batch = std::min(p2, full);
+                }
+            }
             int rc2 = launch_batch(batch);
             if (rc2) return rc2;
             enq += batch;
