@@ -71,7 +71,10 @@ typedef struct b2s_options {
     int persistent;       /* 1: run each batch of pivots as ONE persistent cooperative kernel with device-wide
                              barriers between the phases; 0: three launches per pivot (CUDA graph);
                              2 (default): the loop kernel for tableaux below 32 MB on one GPU, launches otherwise */
-    int reserved[6];
+    int relative_infeasibility; /* 0 (default): the reference's absolute phase-1 test cost[0] <= -1e-9
+                             (src/twoPhaseMethod.cu:265-268); 1: tolerance relative to the magnitude the phase-1
+                             objective started from (the absolute test mis-declares large feasible LPs infeasible) */
+    int reserved[5];
 } b2s_options;
 
 typedef struct b2s_stats {

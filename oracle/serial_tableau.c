@@ -160,6 +160,8 @@ typedef struct {
     uint64_t hash;
     int last_q, last_p;
     double last_cq;
+    int relative_infeasibility; /* opt-in, not reference behaviour: see orc_phase1_verdict */
+    double cost0_phase1_start;  /* cost[0] right after the phase-1 price-out = -(sum of |b_i|) */
 } orc_t;
 
 orc_t *orc_create(int n, int m, const double *A, const double *b, const double *c, int rule, int threads)
@@ -260,7 +262,11 @@ void orc_priceout(orc_t *o)
         }
         o->cost[y] = acc;
     }
+    if (o->phase == 1)
+        o->cost0_phase1_start = o->cost[0];
 }
+
+void orc_set_relative_infeasibility(orc_t *o, int on) { o->relative_infeasibility = on; }
 
 static void trace_push(orc_t *o, int q, int p)
 {
@@ -393,7 +399,14 @@ int orc_iterate(orc_t *o, long budget)
 /* src/twoPhaseMethod.cu:258-282 (:265-268 infeasible test on cost[0], :206-223 degeneracy). */
 int orc_phase1_verdict(const orc_t *o)
 {
-    if (cmp3(o->cost[0], 0.0) < 0)
+    /* Reference: absolute test cost[0] <= -1e-9 (:265-268).  Opt-in alternative (beyond the reference, SURVEY
+     * 8(f)-4): the residual of a feasible phase 1 scales with the magnitude the objective started from, so the
+     * tolerance is taken relative to it: infeasible iff cost[0] < -1e-9 * max(1, |cost[0] at phase-1 start|). */
+    if (o->relative_infeasibility) {
+        const double scale = fmax(1.0, fabs(o->cost0_phase1_start));
+        if (o->cost[0] < -1e-9 * scale)
+            return ORC_INFEASIBLE;
+    } else if (cmp3(o->cost[0], 0.0) < 0)
         return ORC_INFEASIBLE;
     const int lo = o->n + o->m, hi = o->n + 2 * o->m;
     for (int i = 0; i < o->m; ++i)

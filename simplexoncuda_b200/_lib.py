@@ -26,7 +26,7 @@ class Options(C.Structure):
     _fields_ = [("device", C.c_int), ("dtype", C.c_int), ("pivot_rule", C.c_int),
                 ("fold_artificials", C.c_int), ("skip_zero_rows", C.c_int), ("use_graph", C.c_int),
                 ("batch", C.c_int), ("max_pivots", C.c_longlong), ("trace_capacity", C.c_longlong),
-                ("update_variant", C.c_int), ("persistent", C.c_int), ("reserved", C.c_int * 6)]
+                ("update_variant", C.c_int), ("persistent", C.c_int), ("relative_infeasibility", C.c_int), ("reserved", C.c_int * 5)]
 
 
 class Stats(C.Structure):

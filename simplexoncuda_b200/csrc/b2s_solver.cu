@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <chrono>
 #include <climits>
+#include <cmath>
 #include <map>
 #include <cstdarg>
 #include <cstdio>
@@ -146,6 +147,7 @@ struct SolverImpl final : SolverBase {
     int loop_grid = 0;  // persistent loop kernel: co-resident CTAs
     std::map<int, cudaGraphExec_t> graphs;  // captured batches of pivots, keyed by batch length
     long long pivots_p1 = 0, pivots_p2 = 0;
+    double cost0_phase1_start = 0.0;  // relative_infeasibility: cost[0] right after the phase-1 price-out
     double sec_load = 0, sec_p1 = 0, sec_p2 = 0;
 
     // sharding
@@ -689,6 +691,12 @@ struct SolverImpl final : SolverBase {
             priceout_kernel<real><<<blocks, 256, 0, stream>>>(P, coef);
         }
         CK(cudaGetLastError());
+        if (phase == 1 && opt.relative_infeasibility) {  // magnitude the phase-1 objective starts from: -(sum |b_i|)
+            real c0 = 0;
+            CK(cudaMemcpyAsync(&c0, cost, sizeof(real), cudaMemcpyDeviceToHost, stream));
+            CK(cudaStreamSynchronize(stream));
+            cost0_phase1_start = (double)c0;
+        }
         stage = kPriced;
         return B2S_OK;
     }
@@ -918,6 +926,15 @@ struct SolverImpl final : SolverBase {
         int h[2] = {0, 0};
         CK(cudaMemcpyAsync(h, verdict, sizeof(h), cudaMemcpyDeviceToHost, stream));
         CK(cudaStreamSynchronize(stream));
+        if (opt.relative_infeasibility) {
+            // Opt-in, beyond the reference: the residual a feasible phase 1 leaves in cost[0] scales
+            // with the magnitude it started from, so the -1e-9 tolerance is taken relative to that magnitude.
+            real c0 = 0;
+            CK(cudaMemcpyAsync(&c0, cost, sizeof(real), cudaMemcpyDeviceToHost, stream));
+            CK(cudaStreamSynchronize(stream));
+            const double scale = std::max(1.0, std::fabs(cost0_phase1_start));
+            h[0] = ((double)c0 < -1e-9 * scale) ? 1 : 0;
+        }
         *status = h[0] ? B2S_INFEASIBLE : (h[1] > 0 ? B2S_DEGENERATE : B2S_FEASIBLE);
         return B2S_OK;
     }

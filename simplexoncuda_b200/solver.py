@@ -30,7 +30,7 @@ class Solver:
 
     def __init__(self, device=0, dtype=L.F64, pivot_rule=L.RULE_REFERENCE, fold_artificials=True,
                  skip_zero_rows=False, use_graph=True, batch=0, max_pivots=0, trace_capacity=0,
-                 update_variant=8, persistent="auto"):
+                 update_variant=8, persistent="auto", relative_infeasibility=False):
         self.lib = L.load()
         opt = L.Options()
         self.lib.b2s_default_options(C.byref(opt))
@@ -45,6 +45,7 @@ class Solver:
         opt.trace_capacity = trace_capacity
         opt.update_variant = update_variant
         opt.persistent = 2 if persistent in ("auto", None) else int(bool(persistent))
+        opt.relative_infeasibility = int(bool(relative_infeasibility))
         self.h = C.c_void_p()
         rc = self.lib.b2s_create(C.byref(opt), C.byref(self.h))
         if rc != L.OK:

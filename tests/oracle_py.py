@@ -33,6 +33,7 @@ def lib():
         l.orc_phase1_verdict.argtypes = [C.c_void_p]
         l.orc_extract.argtypes = [C.c_void_p, _dp, _dp]
         l.orc_two_phase.argtypes = [C.c_void_p, C.c_long, _dp, _dp]
+        l.orc_set_relative_infeasibility.argtypes = [C.c_void_p, C.c_int]
         l.orc_rows.restype = C.c_long
         l.orc_rows.argtypes = [C.c_void_p]
         l.orc_pivots.restype = C.c_long
@@ -86,7 +87,7 @@ def xorwow_outputs(seed, offset, count):
 class Oracle:
     """Stepping handle over the serial restatement."""
 
-    def __init__(self, A, b, c, rule=0, threads=1, trace_cap=1 << 20):
+    def __init__(self, A, b, c, rule=0, threads=1, trace_cap=1 << 20, relative_infeasibility=False):
         self.A = np.ascontiguousarray(A, dtype=np.float64)
         self.b = np.ascontiguousarray(b, dtype=np.float64)
         self.c = np.ascontiguousarray(c, dtype=np.float64)
@@ -94,6 +95,8 @@ class Oracle:
         self.l = lib()
         self.h = self.l.orc_create(self.n, self.m, self.A.ctypes.data_as(_dp), self.b.ctypes.data_as(_dp),
                                    self.c.ctypes.data_as(_dp), rule, threads)
+        if relative_infeasibility:
+            self.l.orc_set_relative_infeasibility(self.h, 1)
         self._trace = np.zeros((trace_cap, 2), dtype=np.int32)
         self.l.orc_set_trace(self.h, self._trace.ctypes.data_as(_ip), trace_cap)
 

@@ -33,7 +33,7 @@ def test_python_prototypes_match_header():
 
 def test_struct_layouts():
     from simplexoncuda_b200 import _lib
-    # b2s_options: 7 ints, pad, 2 long long, 1+7 ints ; b2s_stats: 13 x 8 bytes
+    # b2s_options: 7 ints, pad, 2 long long, 3 named + 5 reserved ints ; b2s_stats: 13 x 8 bytes
     assert ctypes.sizeof(_lib.Options) == 80
     assert ctypes.sizeof(_lib.Stats) == 104
     opt = _lib.Options()

@@ -294,3 +294,23 @@ def test_call_order_errors(S):
             s.select_entering()                    # price-out first
     with pytest.raises(S.B2SError):
         S.Solver(pivot_rule=7)
+
+
+# ---- opt-in robustness beyond the reference ---------------------------------------------------------
+@pytest.mark.parametrize("seed,n,m,scale", [(1, 24, 16, 1e7), (1, 40, 32, 1e7), (2, 64, 48, 1e9)])
+def test_relative_infeasibility_tolerance(S, seed, n, m, scale):
+    """LPs whose RHS is scaled by 1e7..1e9 are feasible, but the reference's absolute test cost[0] <= -1e-9
+    declares them INFEASIBLE (rounding residue of a huge phase-1 objective).  Default behaviour reproduces that
+    (parity); relative_infeasibility=True solves them, identically to the oracle in the same mode, and the optimum
+    is the unscaled optimum times the scale."""
+    A, b, c = O.generate(n, m, O.seed_triplet(seed, 0), 1, 100)
+    bs = b * scale
+    assert check_solve(S, A, bs, c, max_pivots=5000)["status"] == S.INFEASIBLE
+    ref = O.Oracle(A, bs, c, relative_infeasibility=True).two_phase(max_pivots=5000)
+    with S.Solver(relative_infeasibility=True, max_pivots=5000) as s:
+        s.load(A, bs, c)
+        r = s.solve()
+    assert r["status"] == ref["status"] == 0
+    assert int(r["stats"].trace_hash) == ref["hash"] and r["objective"] == ref["objective"]
+    base = O.Oracle(A, b, c).two_phase()
+    assert abs(r["objective"] - base["objective"] * scale) <= 1e-9 * abs(r["objective"])

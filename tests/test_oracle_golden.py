@@ -193,3 +193,17 @@ def test_lowest_index_and_bland_rules_reach_same_optimum():
     assert ref["status"] == low["status"] == bland["status"] == 0
     assert abs(ref["objective"] - low["objective"]) <= 1e-7 * abs(ref["objective"])
     assert abs(ref["objective"] - bland["objective"]) <= 1e-7 * abs(ref["objective"])
+
+
+def test_relative_infeasibility_mode_oracle():
+    """Opt-in mode beyond the reference: the absolute test mis-declares scaled feasible LPs infeasible."""
+    A, b, c = O.generate(24, 16, O.seed_triplet(1, 0), 1, 100)
+    base = O.Oracle(A, b, c).two_phase()
+    assert base["status"] == 0
+    assert O.Oracle(A, b * 1e7, c).two_phase(max_pivots=5000)["status"] == O.INFEASIBLE
+    rel = O.Oracle(A, b * 1e7, c, relative_infeasibility=True).two_phase(max_pivots=5000)
+    assert rel["status"] == 0 and abs(rel["objective"] - base["objective"] * 1e7) <= 1e-9 * abs(rel["objective"])
+    # a genuinely infeasible LP stays infeasible in both modes
+    p = json.load(open(os.path.join(HERE, "golden", "examples.json")))["infeasibleProblem"]["text"]
+    Ai, bi, ci = parse_lp(p)
+    assert O.Oracle(Ai, bi, ci, relative_infeasibility=True).two_phase()["status"] == O.INFEASIBLE
