@@ -322,6 +322,7 @@ struct SolverImpl final : SolverBase {
             return fail(B2S_ERR_ARG, "sharded solve needs constraints %% (world*512) == 0 (m=%d, world=%d)", m_, world);
         if (world > 1 && (long long)m_ > (long long)kSelBlock * kMaxSlots)
             return fail(B2S_ERR_ARG, "sharded solve supports at most %d constraints", kSelBlock * kMaxSlots);
+        folded = opt.fold_artificials != 0;  // attach() (caller-owned tabular_t) switches folding off for its own use
         n = n_;
         m = m_;
         m_loc = m / world;
@@ -1099,7 +1100,6 @@ struct SolverImpl final : SolverBase {
             return fail(B2S_ERR_ARG, "tableau pitch/base must be 32-byte aligned (cudaMallocPitch guarantees it)");
         CK(cudaSetDevice(dev));
         // scratch sized for this shape; no tableau storage of our own
-        const bool keep_fold = folded;
         folded = false;
         world = 1;
         n = std::max(n_vars, 1);
@@ -1132,7 +1132,6 @@ struct SolverImpl final : SolverBase {
             cap_cols = (size_t)ld_;
             cap_n = (size_t)n;
         }
-        (void)keep_fold;
         ld = ld_;
         R1 = Rs = Rc = rows;
         T = reinterpret_cast<real*>(table);
