@@ -314,3 +314,21 @@ def test_relative_infeasibility_tolerance(S, seed, n, m, scale):
     assert int(r["stats"].trace_hash) == ref["hash"] and r["objective"] == ref["objective"]
     base = O.Oracle(A, b, c).two_phase()
     assert abs(r["objective"] - base["objective"] * scale) <= 1e-9 * abs(r["objective"])
+
+
+# ---- degenerate shapes and data -------------------------------------------------------------------------
+@pytest.mark.parametrize("persistent", [True, False])
+def test_edge_shapes_and_data(S, persistent):
+    rng = np.random.default_rng(5)
+    cases = []
+    for n, m in ((1, 1), (1, 5), (5, 1), (2, 600), (700, 2), (3, 513), (65, 64)):
+        cases.append((rng.integers(1, 9, size=(n, m)).astype(float), rng.integers(1, 9, size=m).astype(float),
+                      rng.integers(1, 9, size=n).astype(float)))
+    A0 = rng.integers(-3, 4, size=(4, 3)).astype(float)
+    cases.append((A0, np.zeros(3), rng.integers(-3, 4, size=4).astype(float)))          # b = 0: fully degenerate vertex
+    cases.append((A0, np.array([1.0, 2.0, 3.0]), np.zeros(4)))                           # zero objective
+    cases.append((np.zeros((4, 3)), np.array([1.0, 2.0, 3.0]), np.array([1.0, 0.0, -1.0, 2.0])))  # A = 0: unbounded
+    cases.append((np.zeros((4, 3)), np.array([1.0, -2.0, 3.0]), np.array([1.0, 0.0, -1.0, 2.0])))  # 0 <= -2: infeasible
+    cases.append((np.full((3, 3), 1e-10), np.ones(3), np.ones(3)))                       # entries below the 1e-9 threshold
+    for A, b, c in cases:
+        check_solve(S, A, b, c, max_pivots=20000, persistent=persistent)
