@@ -35,6 +35,8 @@ extern "C" {
 #define B2S_ERR_NOMEM 4  /* device or host allocation failed              */
 #define B2S_ERR_NCCL 5   /* NCCL error (sharded solves)                   */
 #define B2S_ERR_NOGPU 6  /* no CUDA device: there is no CPU fallback      */
+#define B2S_ERR_PEER 7   /* sharded solve: a peer rank stopped publishing (bounded wait expired); the handle must be
+                            reloaded before it can solve again                                                      */
 
 /* ---- solver statuses (include/twoPhaseMethod.h:5-8, src/solver.cu:77) -------------------- */
 #define B2S_FEASIBLE 0
@@ -61,7 +63,9 @@ typedef struct b2s_options {
     int pivot_rule;       /* B2S_RULE_*                                                               */
     int fold_artificials; /* 1: do not store the artificial rows (they are bitwise copies of the
                              slack rows during phase 1); 0: reference layout with 1+n+2m rows        */
-    int skip_zero_rows;   /* 1: rows whose pivot-constraint entry is exactly 0 are not streamed      */
+    int skip_zero_rows;   /* 1 (default): rows whose pivot-constraint entry a_pr is exactly 0 are neither read nor
+                             written by the rank-1 update -- fma(s_i, 0, x) == x (src/solver.cu:43), so results are
+                             value-identical; 0: stream every stored row (the nominal 2*R*m*sizeof bytes per pivot) */
     int use_graph;        /* 1: replay each batch of pivots as a CUDA graph                          */
     int batch;            /* pivots enqueued between two host status polls; 0 = choose from size     */
     long long max_pivots; /* total pivot cap for b2s_solve_two_phase; <= 0 = none (as the reference) */

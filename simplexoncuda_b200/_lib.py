@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libb2s.so")
 
 # error codes / statuses / options (mirror include/b2s.h)
-OK, ERR_ARG, ERR_STATE, ERR_CUDA, ERR_NOMEM, ERR_NCCL, ERR_NOGPU = range(7)
+OK, ERR_ARG, ERR_STATE, ERR_CUDA, ERR_NOMEM, ERR_NCCL, ERR_NOGPU, ERR_PEER = range(8)
 FEASIBLE, INFEASIBLE, UNBOUNDED, DEGENERATE, ITER_LIMIT, RUNNING = 0, -1, -2, -3, -4, -10
 F64, F32 = 0, 1
 RULE_REFERENCE, RULE_LOWEST, RULE_BLAND = 0, 1, 2

@@ -655,6 +655,8 @@ __global__ void state_reset_kernel(DevState* st, int fresh)
     st->live = 0;
     st->ticket_ratio = 0;
     st->ticket_cost = 0;
+    st->tile_ticket = 0;
+    st->tile_done = 0;
     if (fresh) {
         st->pivots = 0;
         st->hash = 1469598103934665603ULL;

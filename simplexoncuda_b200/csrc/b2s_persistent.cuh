@@ -140,7 +140,14 @@ __global__ void __launch_bounds__(kSelBlock, 1) pivot_loop_kernel(const __grid_c
             }
             __syncthreads();
         }
-        if (!grid_barrier(&st->bar_count, epoch, &s_ok)) break;
+        if (!grid_barrier(&st->bar_count, epoch, &s_ok)) {
+            if (threadIdx.x == 0) {  // a CTA never arrived: make the failure visible to the host instead of looking like progress
+                st->status = kStatusPeerTimeout;
+                st->live = 0;
+                __threadfence();
+            }
+            break;
+        }
         const real *slot_v = P.rslot_v, *slot_max = P.rslot_max;
         const int *slot_i = P.rslot_i, *slot_k = P.rslot_k;
         if (sharded) {
@@ -238,7 +245,14 @@ __global__ void __launch_bounds__(kSelBlock, 1) pivot_loop_kernel(const __grid_c
             for (long long i = gtid; i < P.ld; i += gstride)
                 P.s[i] = (i < P.m_loc && i != lp) ? div_r(-__ldcg(P.col + i), piv) : (real)0;
         }
-        if (!grid_barrier(&st->bar_count, epoch, &s_ok)) break;
+        if (!grid_barrier(&st->bar_count, epoch, &s_ok)) {
+            if (threadIdx.x == 0) {  // a CTA never arrived: make the failure visible to the host instead of looking like progress
+                st->status = kStatusPeerTimeout;
+                st->live = 0;
+                __threadfence();
+            }
+            break;
+        }
         const real* rowp = P.rowp;
         if (sharded) {
             if (owner && blockIdx.x == 0 && threadIdx.x < P.world) {
@@ -259,7 +273,14 @@ __global__ void __launch_bounds__(kSelBlock, 1) pivot_loop_kernel(const __grid_c
             piv = __ldcg(rowp + stored_row(P, 1 + (long long)q));  // a_pq = T[1+q][p]
             for (long long i = gtid; i < P.ld; i += gstride)
                 P.s[i] = (i < P.m_loc && i != lp) ? div_r(-__ldcg(P.col + i), piv) : (real)0;
-            if (!grid_barrier(&st->bar_count, epoch, &s_ok)) break;
+            if (!grid_barrier(&st->bar_count, epoch, &s_ok)) {
+            if (threadIdx.x == 0) {  // a CTA never arrived: make the failure visible to the host instead of looking like progress
+                st->status = kStatusPeerTimeout;
+                st->live = 0;
+                __threadfence();
+            }
+            break;
+        }
         }
         const real sc = div_r(-cq, piv);  // src/solver.cu:54
         if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -270,7 +291,14 @@ __global__ void __launch_bounds__(kSelBlock, 1) pivot_loop_kernel(const __grid_c
         // ---- phase D: cost update + next entering tournament, then the rank-1 update ----------------
         if (blockIdx.x < P.Gc) cost_select_blocks<real, true, true>(P, rowp, sc, sm, &s_flag);
         stream_phase<real, VB, U, SKIP>(P, rowp, &s_next, P.serpentine && (seq & 1ull));
-        if (!grid_barrier(&st->bar_count, epoch, &s_ok)) break;
+        if (!grid_barrier(&st->bar_count, epoch, &s_ok)) {
+            if (threadIdx.x == 0) {  // a CTA never arrived: make the failure visible to the host instead of looking like progress
+                st->status = kStatusPeerTimeout;
+                st->live = 0;
+                __threadfence();
+            }
+            break;
+        }
     }
 }
 

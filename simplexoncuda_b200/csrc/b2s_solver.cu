@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <chrono>
 #include <climits>
+#include <cstddef>
 #include <cmath>
 #include <map>
 #include <cstdarg>
@@ -118,7 +119,7 @@ struct SolverImpl final : SolverBase {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int n = 0, m = 0, m_loc = 0, col0 = 0;
     long long ld = 0, Rs = 0, R1 = 0, Rc = 0;
-    size_t cap_T = 0, cap_rows = 0, cap_cols = 0, cap_n = 0;  // allocated capacities
+    size_t cap_T = 0, cap_rows = 0, cap_cols = 0, cap_n = 0, cap_m = 0;  // allocated capacities
     int phase = 0;
     Stage stage = kEmpty;
     bool folded = true;
@@ -221,7 +222,7 @@ struct SolverImpl final : SolverBase {
         T = cost = col = s = rowp = coef = c_dev = rslot_v = rslot_max = cslot_v = nullptr;
         rslot_i = rslot_k = cslot_i = cslot_k = base = neg = nullptr;
         x_dev = stage_dev = nullptr;
-        cap_T = cap_rows = cap_cols = cap_n = cap_stage = 0;
+        cap_T = cap_rows = cap_cols = cap_n = cap_m = cap_stage = 0;
         stage = kEmpty;
     }
 
@@ -333,7 +334,7 @@ struct SolverImpl final : SolverBase {
         Rc = R1;
         phase = 0;
         const size_t needT = (size_t)Rs * (size_t)ld;
-        if (needT > cap_T || (size_t)R1 > cap_rows || (size_t)ld > cap_cols || (size_t)n > cap_n) {
+        if (needT > cap_T || (size_t)R1 > cap_rows || (size_t)ld > cap_cols || (size_t)n > cap_n || (size_t)m > cap_m) {
             free_problem();
             int rc;
             if ((rc = dmalloc(&T_own, needT))) return rc;
@@ -357,6 +358,7 @@ struct SolverImpl final : SolverBase {
             cap_rows = (size_t)R1;
             cap_cols = (size_t)ld;
             cap_n = (size_t)n;
+            cap_m = (size_t)m;
         }
         T = T_own;
         cost = cost_own;
@@ -396,10 +398,15 @@ struct SolverImpl final : SolverBase {
         static const Variant table[kNumVariants] = {{16, 8, 0, 0}, {16, 8, 1, 0}, {32, 4, 0, 0}, {32, 4, 1, 0}, {32, 8, 0, 0},
                                                     {16, 4, 0, 0}, {16, 8, 2, 0}, {32, 8, 1, 0}, {32, 8, 0, 1}, {32, 4, 0, 1},
                                                     {16, 4, 0, 1}, {32, 8, 1, 1}, {32, 8, 2, 1}, {16, 8, 0, 1}, {32, 8, 0, 1}};
+        return table[variant_index()];
+    }
+    // One index for the tiling (fill_params) and for the kernel (update_fn): a mismatch would leave columns uncovered.
+    int variant_index() const
+    {
         int v = opt.update_variant;
         if (v < 0 || v >= kNumVariants) v = 8;
         if (use_persistent()) v = 8;  // the loop kernel is built for the 256-bit / 8-row / ticketed geometry
-        return table[v];
+        return v;
     }
     // persistent: 0 = three launches per pivot, 1 = loop kernel, 2 = auto.  Measured on B200 on complete solves
     // (profiles/r01_scaling_and_loop_modes.md): the loop kernel wins for small tableaux (47.6k vs 43.2k pivots/s
@@ -426,8 +433,7 @@ struct SolverImpl final : SolverBase {
     }
     UpdateFn update_fn() const
     {
-        int v = opt.update_variant;
-        if (v < 0 || v >= kNumVariants) v = 8;
+        const int v = variant_index();
         switch (v) {
             case 0: return pick_skip<16, 8, 0, false>();
             case 1: return pick_skip<16, 8, 1, false>();
@@ -803,7 +809,7 @@ struct SolverImpl final : SolverBase {
             void* args[] = {&Pk, &bk};
             cudaError_t ce = cudaLaunchCooperativeKernel((const void*)loop_fn(), dim3((unsigned)loop_grid), dim3(kSelBlock),
                                                          args, 0, stream);
-            if (ce == cudaSuccess) return B2S_OK;
+            if (ce == cudaSuccess) return reset_tickets();
             if (ce != cudaErrorCooperativeLaunchTooLarge && ce != cudaErrorLaunchOutOfResources)
                 return fail(B2S_ERR_CUDA, "cooperative launch of the pivot loop kernel: %s", cudaGetErrorString(ce));
             // the SMs cannot host one CTA each right now (another context holds resources): use the other GPU
@@ -811,6 +817,8 @@ struct SolverImpl final : SolverBase {
             cudaGetLastError();
             opt.persistent = 0;
             fill_params();
+            int rc = reset_tickets();
+            if (rc) return rc;
         }
         const bool graphable = opt.use_graph && (world == 1 || p2p);
         if (!graphable) {
@@ -834,6 +842,15 @@ struct SolverImpl final : SolverBase {
             it = graphs.emplace(batch, exec).first;
         }
         CK(cudaGraphLaunch(it->second, stream));
+        return B2S_OK;
+    }
+
+    // The ticket scheduler of the per-launch update kernels re-arms itself; the persistent loop kernel leaves the
+    // counter where its last pivot stopped.  Clear both words before any per-launch kernel may follow it.
+    int reset_tickets()
+    {
+        static_assert(offsetof(DevState, tile_done) == offsetof(DevState, tile_ticket) + sizeof(unsigned), "adjacent");
+        CK(cudaMemsetAsync(&st->tile_ticket, 0, 2 * sizeof(unsigned), stream));
         return B2S_OK;
     }
 
@@ -914,7 +931,20 @@ struct SolverImpl final : SolverBase {
         if (done) *done = made;
         if (status) *status = st_host->status;
         if (st_host->status != kRunning) stage = kPhaseDone;
-        return B2S_OK;
+        return check_device_status();
+    }
+
+    // Only RUNNING / FEASIBLE / UNBOUNDED are legitimate ends of a batch.  Anything else was stored by a bounded wait
+    // that gave up (a peer rank or a CTA never published): the tableau may be half updated, so the solve must stop.
+    int check_device_status()
+    {
+        const int s_ = st_host->status;
+        if (s_ == kRunning || s_ == kFeasible || s_ == kUnbounded) return B2S_OK;
+        stage = kEmpty;  // nothing can continue from this tableau
+        if (s_ == kStatusPeerTimeout)
+            return fail(B2S_ERR_PEER, "rank %d/%d: a peer rank (or a CTA of the loop kernel) did not publish within the bounded wait "
+                                      "during pivot %lld; the tableau is no longer consistent", rank, world, st_host->pivots + 1);
+        return fail(B2S_ERR_CUDA, "device loop stopped with undocumented status %d", s_);
     }
 
     int phase1_verdict(int* status) override
@@ -1107,7 +1137,7 @@ struct SolverImpl final : SolverBase {
         m_loc = m;
         col0 = 0;
         const long long ld_ = (long long)(pitch / sizeof(double));
-        if ((size_t)rows > cap_rows || (size_t)ld_ > cap_cols || (size_t)n > cap_n) {
+        if ((size_t)rows > cap_rows || (size_t)ld_ > cap_cols || (size_t)n > cap_n || (size_t)m > cap_m) {
             free_problem();
             int rc;
             if ((rc = dmalloc(&T_own, 1))) return rc;
@@ -1131,6 +1161,7 @@ struct SolverImpl final : SolverBase {
             cap_rows = (size_t)rows;
             cap_cols = (size_t)ld_;
             cap_n = (size_t)n;
+            cap_m = (size_t)m;
         }
         ld = ld_;
         R1 = Rs = Rc = rows;
@@ -1252,6 +1283,10 @@ struct SolverImpl final : SolverBase {
             flush_bytes = 512ull << 20;
             CK(cudaMalloc(&flush_buf, flush_bytes));
         }
+        {
+            int rc = reset_tickets();
+            if (rc) return rc;
+        }
         const long long work = std::max(Rs, ld);
         bench_fill_kernel<real><<<(unsigned)((work + 255) / 256), 256, 0, stream>>>(P);
         std::vector<cudaEvent_t> ev(2 * (size_t)launches);
@@ -1277,11 +1312,16 @@ struct SolverImpl final : SolverBase {
     // Real pivots, launched one kernel at a time with CUDA events between the three launches.
     int profile_pivots(int count, float* ms_ratio, float* ms_gather, float* ms_update, long long* done) override
     {
+        if (stage == kPhaseDone) {  // the phase ended exactly at the end of the previous chunk: nothing left to time
+            if (done) *done = 0;
+            return B2S_OK;
+        }
         if (stage != kReady) return fail(B2S_ERR_STATE, "profile_pivots follows select_entering / iterate");
         if (world > 1) return fail(B2S_ERR_STATE, "profile_pivots is single-GPU only");
         CK(cudaSetDevice(dev));
         int rc = fetch_state();
         if (rc) return rc;
+        if ((rc = reset_tickets())) return rc;
         const long long start = st_host->pivots;
         const long long limit = start + count;
         CK(cudaMemcpyAsync(&st->limit, &limit, sizeof(long long), cudaMemcpyHostToDevice, stream));
@@ -1362,7 +1402,7 @@ void b2s_default_options(b2s_options* opt)
     opt->dtype = B2S_F64;
     opt->pivot_rule = B2S_RULE_REFERENCE;
     opt->fold_artificials = 1;
-    opt->skip_zero_rows = 0;
+    opt->skip_zero_rows = 1;  /* value-exact (src/solver.cu:43: fma(s_i, 0, x) == x): rows with a_pr == 0 are not streamed */
     opt->use_graph = 1;
     opt->batch = 0;
     opt->max_pivots = 0;

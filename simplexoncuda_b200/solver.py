@@ -29,7 +29,7 @@ class Solver:
     """One device-resident two-phase simplex solver (opaque b2s_solver handle)."""
 
     def __init__(self, device=0, dtype=L.F64, pivot_rule=L.RULE_REFERENCE, fold_artificials=True,
-                 skip_zero_rows=False, use_graph=True, batch=0, max_pivots=0, trace_capacity=0,
+                 skip_zero_rows=True, use_graph=True, batch=0, max_pivots=0, trace_capacity=0,
                  update_variant=8, persistent="auto", relative_infeasibility=False):
         self.lib = L.load()
         opt = L.Options()

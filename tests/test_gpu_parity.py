@@ -164,13 +164,14 @@ def test_blands_rule_breaks_cycling(S):
         assert r["status"] == cs["bland_status"]
 
 
-@pytest.mark.parametrize("opts", [dict(fold_artificials=False), dict(skip_zero_rows=True), dict(use_graph=False),
+@pytest.mark.parametrize("opts", [dict(fold_artificials=False), dict(skip_zero_rows=False), dict(use_graph=False),
                                   dict(update_variant=2), dict(update_variant=4), dict(update_variant=1),
-                                  dict(batch=1), dict(update_variant=7, skip_zero_rows=True), dict(update_variant=4),
-                                  dict(update_variant=10), dict(update_variant=9, skip_zero_rows=True), dict(update_variant=0),
+                                  dict(batch=1), dict(update_variant=7, skip_zero_rows=False), dict(update_variant=4),
+                                  dict(update_variant=10), dict(update_variant=9, skip_zero_rows=False), dict(update_variant=0),
                                   dict(persistent=False), dict(persistent=False, use_graph=False),
-                                  dict(persistent=False, skip_zero_rows=True), dict(persistent=True, batch=3),
-                                  dict(persistent=False, update_variant=14), dict(persistent=False, update_variant=14, fold_artificials=False)])
+                                  dict(persistent=False, skip_zero_rows=False), dict(persistent=True, batch=3), dict(persistent=True, skip_zero_rows=False),
+                                  dict(persistent=False, update_variant=14, skip_zero_rows=False),
+                                  dict(persistent=False, update_variant=14, fold_artificials=False, skip_zero_rows=False)])
 def test_options_do_not_change_results(S, opts):
     A, b, c = O.generate(300, 260, O.seed_triplet(77, 1), 1, 100)
     check_solve(S, A, b, c, **opts)
