@@ -78,7 +78,11 @@ typedef struct b2s_options {
     int relative_infeasibility; /* 0 (default): the reference's absolute phase-1 test cost[0] <= -1e-9
                              (src/twoPhaseMethod.cu:265-268); 1: tolerance relative to the magnitude the phase-1
                              objective started from (the absolute test mis-declares large feasible LPs infeasible) */
-    int reserved[5];
+    int lookahead;        /* 2 (default) / 1: ONE launch per pivot -- helper CTAs of the streaming update select the NEXT pivot
+                             (entering column, ratio test, pivot-constraint gather; sharded: both exchanges over NVLink peer
+                             memory) under the stream, replacing the reference's serial chain src/solver.cu:86-105;
+                             0: three launches per pivot (ratio, gather, update).  Results are bit-identical.            */
+    int reserved[4];
 } b2s_options;
 
 typedef struct b2s_stats {
@@ -180,6 +184,17 @@ int b2s_max_le_zero_device(b2s_solver *s, const double *dvec, long long n, int *
  * share and its achieved HBM bandwidth on live data. */
 int b2s_profile_pivots(b2s_solver *s, int count, float *ms_ratio, float *ms_gather, float *ms_update,
                        long long *pivots_done);
+
+/* How the pivot loop of the current problem runs: *launches_per_pivot (1 = look-ahead kernel, 3 / 4 = separate ratio, gather,
+ * (svec,) update launches, 0 = persistent cooperative loop kernel), *lookahead, *persistent (booleans). */
+int b2s_get_loop_info(b2s_solver *s, int *launches_per_pivot, int *lookahead, int *persistent);
+
+/* Look-ahead kernel only: `count` real pivots launched one at a time; kernel_ms[count] = CUDA-event time of each launch,
+ * stage_us[count*6] = microseconds from kernel start (globaltimer, helper CTA 0 of this rank) to: RHS row done, next entering
+ * variable known, next leaving constraint known (sharded: after exchange 1), next pivot constraint complete on this rank
+ * (sharded: after exchange 2), proposal complete, pivot committed (last CTA left).  Works on sharded solvers: every rank calls
+ * it with the same count. */
+int b2s_profile_lookahead(b2s_solver *s, int count, float *kernel_ms, double *stage_us, long long *pivots_done);
 
 /* ---- sharded solves (constraint slabs over the GPUs of one box) ------------------------------ */
 #define B2S_NCCL_ID_BYTES 128

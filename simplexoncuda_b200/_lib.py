@@ -26,7 +26,8 @@ class Options(C.Structure):
     _fields_ = [("device", C.c_int), ("dtype", C.c_int), ("pivot_rule", C.c_int),
                 ("fold_artificials", C.c_int), ("skip_zero_rows", C.c_int), ("use_graph", C.c_int),
                 ("batch", C.c_int), ("max_pivots", C.c_longlong), ("trace_capacity", C.c_longlong),
-                ("update_variant", C.c_int), ("persistent", C.c_int), ("relative_infeasibility", C.c_int), ("reserved", C.c_int * 5)]
+                ("update_variant", C.c_int), ("persistent", C.c_int), ("relative_infeasibility", C.c_int), ("lookahead", C.c_int),
+                ("reserved", C.c_int * 4)]
 
 
 class Stats(C.Structure):
@@ -74,6 +75,8 @@ SIGNATURES = {
     "b2s_ratio_min_device": (C.c_int, [_P, C.c_void_p, C.c_void_p, C.c_longlong, _D, C.POINTER(C.c_uint)]),
     "b2s_max_le_zero_device": (C.c_int, [_P, C.c_void_p, C.c_longlong, _I]),
     "b2s_profile_pivots": (C.c_int, [_P, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), _LL]),
+    "b2s_get_loop_info": (C.c_int, [_P, _I, _I, _I]),
+    "b2s_profile_lookahead": (C.c_int, [_P, C.c_int, C.POINTER(C.c_float), _D, _LL]),
     "b2s_dist_unique_id": (C.c_int, [C.c_char_p]),
     "b2s_dist_init": (C.c_int, [_P, C.c_int, C.c_int, C.c_char_p]),
 }

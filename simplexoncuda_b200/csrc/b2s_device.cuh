@@ -19,6 +19,8 @@
 
 namespace b2s {
 
+struct LaState;
+
 constexpr int kRunning = -10;
 constexpr int kFeasible = 0;
 constexpr int kUnbounded = -2;
@@ -261,6 +263,20 @@ struct PivotParams {
     int nchunks;    // column chunks per row
     int tile_groups;  // unrolled row groups per tile
     long long ntiles;
+    // look-ahead pivot kernel (b2s_lookahead.cuh)
+    LaState* la;
+    unsigned* tile_rec;     // per tile: pivot number of the last update that completed it
+    real* col2;             // 2 x ld: entering column of the prepared pivot, by pivot parity
+    real* s2;               // 2 x ld: -a_q / pivot
+    real* rowp2;            // 2 x rowp_stride: raw pivot constraint (one GPU; sharded solves use the arenas)
+    int* rowlist;           // 2 x rowp_stride: stored rows the update streams (ascending), by pivot parity
+    real* rowval;           // 2 x rowp_stride: their pivot-constraint entries a_pr
+    int* rowpos;            // 2 x rowp_stride: row -> position in rowlist, -1 when the row is not streamed
+    long long rowp_stride;
+    long long wait_cycles;  // bound of every device-side wait (clock64 ticks)
+    int helpers;            // CTAs of the update kernel that run the look-ahead chain before they stream
+    int fault_rank;         // fault injection (tests): this rank stops publishing from pivot fault_pivot on
+    long long fault_pivot;
 };
 
 template <typename real>

@@ -8,6 +8,7 @@
 #include "b2s_kernels.cuh"
 #include "b2s_p2p.cuh"
 #include "b2s_persistent.cuh"
+#include "b2s_lookahead.cuh"
 #include "b2s_bulk.cuh"
 
 #include <algorithm>
@@ -61,6 +62,8 @@ struct SolverBase {
     virtual int bench_update(int launches, int flush, float* ms, double* bytes) = 0;
     virtual int dist_init(int rank, int world, const char* id) = 0;
     virtual int profile_pivots(int count, float* ms_ratio, float* ms_gather, float* ms_update, long long* done) = 0;
+    virtual int profile_lookahead(int count, float* kernel_ms, double* stage_us, long long* done) = 0;
+    virtual int loop_info(int* launches, int* lookahead, int* persistent) = 0;
 
     int fail(int code, const char* fmt, ...)
     {
@@ -142,6 +145,18 @@ struct SolverImpl final : SolverBase {
     void* flush_buf = nullptr;
     size_t flush_bytes = 0;
 
+    // look-ahead pivot kernel (b2s_lookahead.cuh)
+    LaState* la = nullptr;
+    unsigned* tile_rec = nullptr;
+    size_t cap_tiles = 0;
+    real *col2 = nullptr, *s2 = nullptr, *rowp2 = nullptr, *rowval = nullptr;
+    int *rowlist = nullptr, *rowpos = nullptr;
+    int la_grid = 0;
+    int la_helpers = 8;
+    long long wait_cycles = 4000000000ll;
+    int fault_rank = -1;
+    long long fault_pivot = 0;
+
     PivotParams<real> P{};
     int upd_grid = 0;
     size_t upd_smem = 0;  // dynamic shared memory of the update kernel (bulk-copy variant only)
@@ -171,6 +186,8 @@ struct SolverImpl final : SolverBase {
         invalidate_graph();
         free_problem();
         cudaFree(st);
+        cudaFree(la);
+        la = nullptr;
         cudaFreeHost(st_host);
         cudaFree(trace);
         cudaFree(jump_tables);
@@ -219,6 +236,17 @@ struct SolverImpl final : SolverBase {
         cudaFree(neg);
         cudaFree(x_dev);
         cudaFree(stage_dev);
+        cudaFree(tile_rec);
+        cudaFree(col2);
+        cudaFree(s2);
+        cudaFree(rowp2);
+        cudaFree(rowval);
+        cudaFree(rowlist);
+        cudaFree(rowpos);
+        tile_rec = nullptr;
+        col2 = s2 = rowp2 = rowval = nullptr;
+        rowlist = rowpos = nullptr;
+        cap_tiles = 0;
         T = cost = col = s = rowp = coef = c_dev = rslot_v = rslot_max = cslot_v = nullptr;
         rslot_i = rslot_k = cslot_i = cslot_k = base = neg = nullptr;
         x_dev = stage_dev = nullptr;
@@ -240,6 +268,12 @@ struct SolverImpl final : SolverBase {
         CK(cudaEventCreate(&ev1));
         CK(cudaMalloc(&st, sizeof(DevState)));
         CK(cudaMemsetAsync(st, 0, sizeof(DevState), stream));  // `stream` is non-blocking: never mix in legacy-stream calls
+        CK(cudaMalloc(&la, sizeof(LaState)));
+        CK(cudaMemsetAsync(la, 0, sizeof(LaState), stream));
+        if (const char* e = getenv("B2S_LA_HELPERS")) la_helpers = std::max(1, std::min(kLaMaxHelpers, atoi(e)));
+        if (const char* e = getenv("B2S_PEER_TIMEOUT_MS")) wait_cycles = std::max(1ll, atoll(e)) * 2000000ll;  // ~2 GHz
+        if (const char* e = getenv("B2S_FAULT_RANK")) fault_rank = atoi(e);
+        if (const char* e = getenv("B2S_FAULT_PIVOT")) fault_pivot = atoll(e);
         CK(cudaHostAlloc(&st_host, 3 * sizeof(DevState), cudaHostAllocDefault));
         CK(cudaEventCreateWithFlags(&poll_ev[0], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&poll_ev[1], cudaEventDisableTiming));
@@ -354,6 +388,12 @@ struct SolverImpl final : SolverBase {
             if ((rc = dmalloc(&cslot_v, kMaxSlots))) return rc;
             if ((rc = dmalloc(&cslot_i, kMaxSlots))) return rc;
             if ((rc = dmalloc(&cslot_k, kMaxSlots))) return rc;
+            if ((rc = dmalloc(&col2, 2 * (size_t)ld))) return rc;
+            if ((rc = dmalloc(&s2, 2 * (size_t)ld))) return rc;
+            if ((rc = dmalloc(&rowp2, 2 * (size_t)R1))) return rc;
+            if ((rc = dmalloc(&rowval, 2 * (size_t)R1))) return rc;
+            if ((rc = dmalloc(&rowlist, 2 * (size_t)R1))) return rc;
+            if ((rc = dmalloc(&rowpos, 2 * (size_t)R1))) return rc;
             cap_T = needT;
             cap_rows = (size_t)R1;
             cap_cols = (size_t)ld;
@@ -418,6 +458,18 @@ struct SolverImpl final : SolverBase {
         if (opt.persistent == 0 || (world > 1 && !p2p)) return false;
         if (opt.persistent == 1) return true;
         return world == 1 && (double)Rs * (double)ld * sizeof(real) < 32e6;
+    }
+    // lookahead: 0 = three launches per pivot (ratio, gather, update), 1/2 = ONE launch per pivot whose helper CTAs prepare
+    // the next pivot under the streaming update (b2s_lookahead.cuh) whenever the geometry allows it.
+    bool use_lookahead() const
+    {
+        int mode = opt.lookahead;
+        if (const char* e = getenv("B2S_LOOKAHEAD")) mode = atoi(e);
+        if (mode == 0 || use_persistent() || variant_index() != 8) return false;
+        if (world > 1 && !p2p) return false;
+        if ((long long)m > (long long)kSelBlock * kMaxSlots) return false;          // one ratio element per helper thread
+        if (R1 >= (long long)kRowMask - 1 || ld >= (long long)kNoColumn - 1) return false;  // ticket-word fields
+        return true;
     }
     typedef void (*LoopFn)(PivotParams<real>, int);
     LoopFn loop_fn() const
@@ -524,6 +576,34 @@ struct SolverImpl final : SolverBase {
             upd_smem = (size_t)kBulkStages * kBulkRows * kBulkCols * 8;
             cudaFuncSetAttribute(update_bulk_kernel<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)upd_smem);
             upd_grid = num_sms;
+        }
+        // look-ahead kernel: same tile geometry as variant 8; tiles are cut from the per-pivot row list, so size by the maximum
+        {
+            const long long rows_tile8 = (long long)rpp * 8;
+            const long long max_tiles = ((R1 + rows_tile8 - 1) / rows_tile8 + 1) * P.nchunks;
+            if ((size_t)max_tiles > cap_tiles) {
+                cudaFree(tile_rec);
+                tile_rec = nullptr;
+                cap_tiles = 0;
+                if (cudaMalloc(&tile_rec, sizeof(unsigned) * (size_t)max_tiles) == cudaSuccess) {
+                    cap_tiles = (size_t)max_tiles;
+                    cudaMemsetAsync(tile_rec, 0, sizeof(unsigned) * cap_tiles, stream);
+                }
+            }
+            la_grid = (int)std::max<long long>(1, std::min<long long>(num_sms, std::max<long long>(max_tiles + la_helpers, P.Gc)));
+            P.helpers = std::min(la_helpers, la_grid);
+            P.la = la;
+            P.tile_rec = tile_rec;
+            P.col2 = col2;
+            P.s2 = s2;
+            P.rowp2 = rowp2;
+            P.rowlist = rowlist;
+            P.rowval = rowval;
+            P.rowpos = rowpos;
+            P.rowp_stride = (long long)cap_rows;
+            P.wait_cycles = wait_cycles;
+            P.fault_rank = fault_rank;
+            P.fault_pivot = fault_pivot;
         }
         if (opt.persistent) {
             int occ_l = 0;
@@ -665,6 +745,10 @@ struct SolverImpl final : SolverBase {
         negate_kernel<real><<<num_sms * 4, 256, 0, stream>>>(P, neg);
         state_reset_kernel<<<1, 1, 0, stream>>>(st, 1);
         CK(cudaGetLastError());
+        {
+            int rc = reset_lookahead();
+            if (rc) return rc;
+        }
 #ifdef B2S_WITH_NCCL
         if (p2p) {
             // pivot sequence numbers restart at 1: clear this rank's flags, then make sure every rank
@@ -721,6 +805,11 @@ struct SolverImpl final : SolverBase {
 
     int enqueue_pivot()
     {
+        if (use_lookahead()) {
+            // one launch per pivot: streaming update + the next pivot's selection (and, sharded, its two exchanges) under it
+            update_la_kernel<real><<<la_grid, kSelBlock, 0, stream>>>(P);
+            return B2S_OK;
+        }
         if (world > 1 && p2p) {
             // exchanges done by the kernels themselves over NVLink peer memory (b2s_p2p.cuh)
             ratio_p2p_kernel<real><<<P.Gm_loc, kSelBlock, 0, stream>>>(P);
@@ -845,6 +934,29 @@ struct SolverImpl final : SolverBase {
         return B2S_OK;
     }
 
+    // Look-ahead state: proposals, ticket word and tile records restart with the pivot counter.
+    int reset_lookahead()
+    {
+        CK(cudaMemsetAsync(la, 0, sizeof(LaState), stream));
+        if (tile_rec && cap_tiles) CK(cudaMemsetAsync(tile_rec, 0, sizeof(unsigned) * cap_tiles, stream));
+        return B2S_OK;
+    }
+    // First pivot of a phase / of an iterate() call: the helpers' chain on the quiescent tableau (no-op when the previous
+    // update left a complete proposal), then its verdict (unbounded at once, silent peer).
+    int enqueue_prologue()
+    {
+        la_prologue_kernel<real><<<P.helpers, kSelBlock, 0, stream>>>(P);
+        la_prologue_commit_kernel<real><<<1, 1, 0, stream>>>(P);
+        CK(cudaGetLastError());
+        return B2S_OK;
+    }
+    int enqueue_flush()
+    {
+        la_flush_kernel<real><<<(unsigned)std::min<long long>((Rs + 255) / 256, 4 * num_sms), 256, 0, stream>>>(P);
+        CK(cudaGetLastError());
+        return B2S_OK;
+    }
+
     // The ticket scheduler of the per-launch update kernels re-arms itself; the persistent loop kernel leaves the
     // counter where its last pivot stopped.  Clear both words before any per-launch kernel may follow it.
     int reset_tickets()
@@ -876,6 +988,8 @@ struct SolverImpl final : SolverBase {
         const long long limit = max_pivots < 0 ? LLONG_MAX : start + max_pivots;
         CK(cudaMemcpyAsync(&st->limit, &limit, sizeof(long long), cudaMemcpyHostToDevice, stream));
         CK(cudaEventRecord(ev0, stream));
+        const bool la_on = use_lookahead();
+        if (la_on && (rc = enqueue_prologue())) return rc;
         // Batches are enqueued one ahead of the status poll, so the device never idles while the host
         // looks at the state; a batch enqueued after the phase ended (or the budget ran out) costs only
         // its early-exit launches because every kernel checks the device-resident status/limit first.
@@ -915,6 +1029,7 @@ struct SolverImpl final : SolverBase {
             }
             slot ^= 1;
         }
+        if (la_on && (rc = enqueue_flush())) return rc;
         if ((rc = fetch_state())) return rc;
         CK(cudaEventRecord(ev1, stream));
         CK(cudaEventSynchronize(ev1));
@@ -983,6 +1098,17 @@ struct SolverImpl final : SolverBase {
         phase2_costs_kernel<real><<<(unsigned)(((long long)n + m + 255) / 256), 256, 0, stream>>>(P, c_dev);
         state_reset_kernel<<<1, 1, 0, stream>>>(st, 0);  // back to RUNNING, keep counters / hash
         CK(cudaGetLastError());
+        {
+            int rc = reset_lookahead();
+            if (rc) return rc;
+        }
+#ifdef B2S_WITH_NCCL
+        if (p2p) {
+            // a proposal prepared but not executed in phase 1 has left flags with the next pivot's number in the arenas
+            CK(cudaMemsetAsync(arena, 0, sizeof(ArenaHeader<real>), stream));
+            NK(ncclAllReduce(verdict, verdict, 1, ncclInt, ncclSum, comm, stream));
+        }
+#endif
         stage = kBuilt;
         return B2S_OK;
     }
@@ -1157,6 +1283,12 @@ struct SolverImpl final : SolverBase {
             if ((rc = dmalloc(&cslot_v, kMaxSlots))) return rc;
             if ((rc = dmalloc(&cslot_i, kMaxSlots))) return rc;
             if ((rc = dmalloc(&cslot_k, kMaxSlots))) return rc;
+            if ((rc = dmalloc(&col2, 2 * (size_t)ld_))) return rc;
+            if ((rc = dmalloc(&s2, 2 * (size_t)ld_))) return rc;
+            if ((rc = dmalloc(&rowp2, 2 * (size_t)rows))) return rc;
+            if ((rc = dmalloc(&rowval, 2 * (size_t)rows))) return rc;
+            if ((rc = dmalloc(&rowlist, 2 * (size_t)rows))) return rc;
+            if ((rc = dmalloc(&rowpos, 2 * (size_t)rows))) return rc;
             cap_T = 0;
             cap_rows = (size_t)rows;
             cap_cols = (size_t)ld_;
@@ -1176,6 +1308,10 @@ struct SolverImpl final : SolverBase {
         CK(cudaMemsetAsync(st, 0, sizeof(DevState), stream));
         state_reset_kernel<<<1, 1, 0, stream>>>(st, 1);
         CK(cudaGetLastError());
+        {
+            int rc = reset_lookahead();
+            if (rc) return rc;
+        }
         stage = kBuilt;
         return B2S_OK;
     }
@@ -1317,7 +1453,14 @@ struct SolverImpl final : SolverBase {
             return B2S_OK;
         }
         if (stage != kReady) return fail(B2S_ERR_STATE, "profile_pivots follows select_entering / iterate");
-        if (world > 1) return fail(B2S_ERR_STATE, "profile_pivots is single-GPU only");
+        if (use_lookahead()) {
+            // one launch per pivot: the whole pivot is the "update" column
+            int rc = profile_lookahead(count, ms_update, nullptr, done);
+            const long long k = done ? *done : 0;
+            for (long long i = 0; i < k; ++i) ms_ratio[i] = ms_gather[i] = 0.f;
+            return rc;
+        }
+        if (world > 1) return fail(B2S_ERR_STATE, "profile_pivots is single-GPU only without the look-ahead kernel");
         CK(cudaSetDevice(dev));
         int rc = fetch_state();
         if (rc) return rc;
@@ -1350,6 +1493,65 @@ struct SolverImpl final : SolverBase {
         if (done) *done = made;
         if (st_host->status != kRunning) stage = kPhaseDone;
         return B2S_OK;
+    }
+
+    int loop_info(int* launches, int* lookahead, int* persistent) override
+    {
+        const bool la_on = stage != kEmpty && use_lookahead();
+        const bool pers = stage != kEmpty && use_persistent();
+        if (launches) *launches = pers ? 0 : (la_on ? 1 : (world > 1 ? 4 : 3));
+        if (lookahead) *lookahead = la_on ? 1 : 0;
+        if (persistent) *persistent = pers ? 1 : 0;
+        return B2S_OK;
+    }
+
+    // Look-ahead kernel, one launch at a time, with the chain's globaltimer stamps read back after each pivot.
+    int profile_lookahead(int count, float* kernel_ms, double* stage_us, long long* done) override
+    {
+        if (stage == kPhaseDone) {
+            if (done) *done = 0;
+            return B2S_OK;
+        }
+        if (stage != kReady) return fail(B2S_ERR_STATE, "profile_lookahead follows select_entering / iterate");
+        if (!use_lookahead()) return fail(B2S_ERR_STATE, "the look-ahead kernel is not in use for this problem");
+        CK(cudaSetDevice(dev));
+        int rc = fetch_state();
+        if (rc) return rc;
+        const long long start = st_host->pivots;
+        const long long limit = start + count;
+        CK(cudaMemcpyAsync(&st->limit, &limit, sizeof(long long), cudaMemcpyHostToDevice, stream));
+        if ((rc = enqueue_prologue())) return rc;
+        std::vector<cudaEvent_t> ev(2 * (size_t)count);
+        for (auto& e : ev) CK(cudaEventCreate(&e));
+        std::vector<LaState> snap((size_t)count);
+        long long made = 0;
+        for (int k = 0; k < count; ++k) {
+            CK(cudaEventRecord(ev[2 * k], stream));
+            update_la_kernel<real><<<la_grid, kSelBlock, 0, stream>>>(P);
+            CK(cudaEventRecord(ev[2 * k + 1], stream));
+            if (stage_us) {   // the stamps are per pivot: read them before the next launch overwrites them
+                CK(cudaMemcpyAsync(&snap[(size_t)k], la, sizeof(LaState), cudaMemcpyDeviceToHost, stream));
+                CK(cudaStreamSynchronize(stream));
+            }
+        }
+        CK(cudaGetLastError());
+        if ((rc = enqueue_flush())) return rc;
+        if ((rc = fetch_state())) return rc;
+        made = st_host->pivots - start;
+        for (long long k = 0; k < made; ++k) {
+            CK(cudaEventElapsedTime(kernel_ms + k, ev[2 * k], ev[2 * k + 1]));
+            if (stage_us) {
+                const unsigned long long* t = snap[(size_t)k].stamps;
+                const int order[6] = {1, 2, 3, 4, 5, 6};
+                for (int j = 0; j < 6; ++j)
+                    stage_us[6 * k + j] = t[order[j]] >= t[0] ? (double)(t[order[j]] - t[0]) * 1e-3 : -1.0;
+            }
+        }
+        for (auto& e : ev) cudaEventDestroy(e);
+        if (phase == 2) pivots_p2 += made; else pivots_p1 += made;
+        if (done) *done = made;
+        if (st_host->status != kRunning) stage = kPhaseDone;
+        return check_device_status();
     }
 
     int dist_init(int rank_, int world_, const char* id) override
@@ -1409,6 +1611,7 @@ void b2s_default_options(b2s_options* opt)
     opt->trace_capacity = 0;
     opt->update_variant = 8;
     opt->persistent = 2;
+    opt->lookahead = 2;
 }
 
 int b2s_device_count(void)
@@ -1513,6 +1716,13 @@ int b2s_profile_pivots(b2s_solver* s, int count, float* ms_ratio, float* ms_gath
 {
     if (count < 1 || !ms_ratio || !ms_gather || !ms_update) return B2S_ERR_ARG;
     B2S_FWD(profile_pivots(count, ms_ratio, ms_gather, ms_update, pivots_done));
+}
+
+int b2s_get_loop_info(b2s_solver* s, int* launches_per_pivot, int* lookahead, int* persistent) { B2S_FWD(loop_info(launches_per_pivot, lookahead, persistent)); }
+int b2s_profile_lookahead(b2s_solver* s, int count, float* kernel_ms, double* stage_us, long long* pivots_done)
+{
+    if (count < 1 || !kernel_ms) return B2S_ERR_ARG;
+    B2S_FWD(profile_lookahead(count, kernel_ms, stage_us, pivots_done));
 }
 
 int b2s_dist_unique_id(char id[B2S_NCCL_ID_BYTES])

@@ -30,7 +30,7 @@ class Solver:
 
     def __init__(self, device=0, dtype=L.F64, pivot_rule=L.RULE_REFERENCE, fold_artificials=True,
                  skip_zero_rows=True, use_graph=True, batch=0, max_pivots=0, trace_capacity=0,
-                 update_variant=8, persistent="auto", relative_infeasibility=False):
+                 update_variant=8, persistent="auto", relative_infeasibility=False, lookahead="auto"):
         self.lib = L.load()
         opt = L.Options()
         self.lib.b2s_default_options(C.byref(opt))
@@ -46,6 +46,7 @@ class Solver:
         opt.update_variant = update_variant
         opt.persistent = 2 if persistent in ("auto", None) else int(bool(persistent))
         opt.relative_infeasibility = int(bool(relative_infeasibility))
+        opt.lookahead = 2 if lookahead in ("auto", None) else int(bool(lookahead))
         self.h = C.c_void_p()
         rc = self.lib.b2s_create(C.byref(opt), C.byref(self.h))
         if rc != L.OK:
@@ -182,6 +183,40 @@ class Solver:
         self._ck(self.lib.b2s_profile_pivots(self.h, count, a, b, u, C.byref(done)))
         k = done.value
         return {"ratio_ms": np.array(a[:k]), "gather_ms": np.array(b[:k]), "update_ms": np.array(u[:k]), "pivots": k}
+
+    def profile_lookahead(self, count, stages=True):
+        """`count` pivots of the look-ahead kernel, one launch each: kernel ms + the chain's stage times (us from kernel start)."""
+        ms = (C.c_float * count)(); us = (C.c_double * (6 * count))(); done = C.c_longlong()
+        self._ck(self.lib.b2s_profile_lookahead(self.h, count, ms, us if stages else None, C.byref(done)))
+        k = done.value
+        out = {"kernel_ms": np.array(ms[:k]), "pivots": k}
+        if stages:
+            a = np.array(us[:6 * k]).reshape(k, 6)
+            for j, name in enumerate(("rhs_row_us", "entering_known_us", "leaving_known_us", "pivot_row_complete_us",
+                                      "proposal_ready_us", "committed_us")):
+                out[name] = a[:, j]
+        return out
+
+    def loop_info(self):
+        a = C.c_int(); b = C.c_int(); c = C.c_int()
+        self._ck(self.lib.b2s_get_loop_info(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return {"launches_per_pivot": a.value, "lookahead": bool(b.value), "persistent": bool(c.value)}
+
+    def loop_mode(self):
+        i = self.loop_info()
+        if i["persistent"]:
+            return "persistent cooperative loop kernel (1 launch per batch of pivots)"
+        if i["lookahead"]:
+            return "look-ahead kernel: 1 launch per pivot (streaming update + next pivot's selection under it), CUDA graph"
+        return f"{i['launches_per_pivot']} launches per pivot replayed as a CUDA graph"
+
+    def launches_per_pivot(self):
+        return self.loop_info()["launches_per_pivot"]
+
+    def update_kernel_name(self):
+        if self.loop_info()["lookahead"]:
+            return "update_la_kernel (rank-1 update streamed over the row list + cost update + complete selection of the next pivot)"
+        return "update_kernel (fused rank-1 update + cost update + entering tournament)"
 
     # ---- sharding --------------------------------------------------------------------------------
     def dist_init(self, rank, world, unique_id):

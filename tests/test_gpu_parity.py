@@ -58,15 +58,17 @@ def test_generator_matches_oracle(S, n, m, lo, hi):
 
 
 # ---- stepping parity: every intermediate state -----------------------------------------------------
-@pytest.mark.parametrize("persistent", [True, False])
+@pytest.mark.parametrize("loop", ["persistent", "lookahead", "launches", "lookahead-noskip"])
 @pytest.mark.parametrize("fold", [True, False])
 @pytest.mark.parametrize("n,m,lo,hi,seed", [(24, 16, -100, 100, 3), (64, 64, 1, 100, 5), (100, 130, -100, 100, 9),
-                                            (600, 520, 1, 100, 11)])
-def test_stepping_bit_exact(S, persistent, fold, n, m, lo, hi, seed):
+                                            (600, 520, 1, 100, 11), (300, 2500, 1, 100, 13)])
+def test_stepping_bit_exact(S, loop, fold, n, m, lo, hi, seed):
     A, b, c = O.generate(n, m, O.seed_triplet(seed, 0), lo, hi)
     o = O.Oracle(A, b, c)
-    with S.Solver(fold_artificials=fold, use_graph=False, persistent=persistent) as s:
+    with S.Solver(fold_artificials=fold, use_graph=False, persistent=(loop == "persistent"),
+                  lookahead=loop.startswith("lookahead"), skip_zero_rows=(loop != "lookahead-noskip")) as s:
         s.load(A, b, c)
+        assert s.loop_info()["lookahead"] == loop.startswith("lookahead")
         s.build_phase1(); o.build_phase1()
         assert same(s.tableau(), o.tableau()) and same(s.costs(), o.costs()) and same(s.basis(), o.basis())
         s.price_out(); o.priceout()
@@ -170,6 +172,10 @@ def test_blands_rule_breaks_cycling(S):
                                   dict(update_variant=10), dict(update_variant=9, skip_zero_rows=False), dict(update_variant=0),
                                   dict(persistent=False), dict(persistent=False, use_graph=False),
                                   dict(persistent=False, skip_zero_rows=False), dict(persistent=True, batch=3), dict(persistent=True, skip_zero_rows=False),
+                                  dict(persistent=False, lookahead=False), dict(persistent=False, lookahead=False, skip_zero_rows=False),
+                                  dict(persistent=False, lookahead=False, use_graph=False, batch=2),
+                                  dict(persistent=False, lookahead=True, batch=1), dict(persistent=False, lookahead=True, use_graph=False),
+                                  dict(persistent=False, lookahead=True, fold_artificials=False, skip_zero_rows=False),
                                   dict(persistent=False, update_variant=14, skip_zero_rows=False),
                                   dict(persistent=False, update_variant=14, fold_artificials=False, skip_zero_rows=False)])
 def test_options_do_not_change_results(S, opts):
@@ -177,6 +183,36 @@ def test_options_do_not_change_results(S, opts):
     check_solve(S, A, b, c, **opts)
     A, b, c = O.generate(90, 70, O.seed_triplet(5, 0), -100, 100)
     check_solve(S, A, b, c, max_pivots=100000, **opts)
+
+
+@pytest.mark.parametrize("helpers", [1, 3, 16])
+def test_lookahead_helper_counts(S, helpers, monkeypatch):
+    """The look-ahead chain split over 1, 3 or 16 helper CTAs (default 8) gives the same pivots."""
+    monkeypatch.setenv("B2S_LA_HELPERS", str(helpers))
+    A, b, c = O.generate(300, 2600, O.seed_triplet(21, 1), 1, 100)
+    check_solve(S, A, b, c, persistent=False, lookahead=True, max_pivots=400)
+    A, b, c = O.generate(90, 70, O.seed_triplet(5, 0), -100, 100)
+    check_solve(S, A, b, c, max_pivots=100000, persistent=False, lookahead=True)
+
+
+@pytest.mark.parametrize("chunk", [2, 7])
+def test_lookahead_chunked_iterate_bit_exact(S, chunk):
+    """iterate(k) in chunks: the proposal prepared by the last kernel of one call is consumed by the first kernel of the next,
+    and the tableau the host sees in between (after the flush of the held-old pivot column) equals the oracle's."""
+    A, b, c = O.generate(200, 1100, O.seed_triplet(4, 1), 1, 100)
+    o = O.Oracle(A, b, c)
+    with S.Solver(persistent=False, lookahead=True) as s:
+        s.load(A, b, c)
+        s.build_phase1(); o.build_phase1()
+        s.price_out(); o.priceout()
+        s.select_entering()
+        for _ in range(12):
+            st_s, done = s.iterate(chunk)
+            st_o = o.iterate(chunk)
+            assert done == chunk and st_s == S.RUNNING and st_o == O.CONTINUE
+            assert same(s.tableau(), o.tableau()) and same(s.costs(), o.costs()) and same(s.basis(), o.basis())
+        qp, cnt, h = s.trace()
+        assert same(qp, o.trace()) and h == o.hash()
 
 
 # ---- published golden vectors at sizes the oracle needs minutes for --------------------------------
