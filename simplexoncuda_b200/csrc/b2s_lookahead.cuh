@@ -146,6 +146,15 @@ __device__ __forceinline__ long long la_ticket_of(const PivotParams<real>& P, lo
     return reverse ? (P.ntiles - 1 - tmap) : tmap;
 }
 
+// Double-buffered staging of a tile's list entries (tile_rows <= 512 >> 0 ... bounded by kLaMaxTileRows) and ticket words.
+constexpr int kLaMaxTileRows = 512;
+template <typename real>
+struct LaTileSmem {
+    unsigned long long word[2];
+    int row[2][kLaMaxTileRows];
+    real val[2][kLaMaxTileRows];
+};
+
 struct LaShared {
     unsigned long long next_word;
     int ok;
@@ -650,6 +659,7 @@ __global__ void __launch_bounds__(kSelBlock, 1) update_la_kernel(const __grid_co
     __shared__ TreeSmem<real> sm;
     __shared__ real smax[32];
     __shared__ LaShared sh;
+    __shared__ LaTileSmem<real> ts;
 
     DevState* st = P.st;
     LaState* la = P.la;
@@ -683,6 +693,9 @@ __global__ void __launch_bounds__(kSelBlock, 1) update_la_kernel(const __grid_co
                              (long long)ntiles, sm, smax, sh);
 
     // ---- streaming ---------------------------------------------------------------------------------------
+    // One barrier per tile.  While the tile's 256-bit loads are in flight, warp 0 receives the next ticket word and
+    // stages the next tile's list entries (row index, a_pr) in shared memory, so no thread ever waits for a dependent
+    // global load before it can issue its tile loads.
     {
         const int* rlist = P.rowlist + (size_t)par * P.rowp_stride;
         const real* rval = P.rowval + (size_t)par * P.rowp_stride;
@@ -690,85 +703,96 @@ __global__ void __launch_bounds__(kSelBlock, 1) update_la_kernel(const __grid_co
         const int ty = threadIdx.x >> P.log2_tpr;
         const int chunk_cols = EPT << P.log2_tpr;
         const int base = (int)gridDim.x - H;
-        int tile;
-        int skip_row = -1, skip_col = -1;   // publications that preceded the claim of the current tile
-        if (helper) {
-            if (threadIdx.x == 0) sh.next_word = atomicAdd(&la->word, 1ull);
-            __syncthreads();
-            const unsigned long long w = sh.next_word;
-            __syncthreads();
-            tile = (int)(w & kTicketMask) + base;
-            skip_row = (int)((w >> kTicketBits) & kRowMask) - 1;
-            skip_col = (int)(w >> kColShift) - 1;
-        } else {
-            tile = (int)blockIdx.x - H;
+        int buf = 0;
+        if (threadIdx.x == 0) {
+            // helpers have no implicit tile: their first claim is an ordinary one (and sees both publications)
+            ts.word[0] = helper ? atomicAdd(&la->word, 1ull) : 0ull;
         }
+        __syncthreads();
+        int tile, skip_row, skip_col;
+        {
+            const unsigned long long w = ts.word[0];
+            tile = helper ? (int)(w & kTicketMask) + base : (int)blockIdx.x - H;
+            skip_row = helper ? (int)((w >> kTicketBits) & kRowMask) - 1 : -1;
+            skip_col = helper ? (int)(w >> kColShift) - 1 : -1;
+        }
+        if (tile < ntiles) {
+            const int tmap0 = reverse ? (ntiles - 1 - tile) : tile;
+            const int rb0 = tmap0 / P.nchunks;
+            for (int e = threadIdx.x; e < tile_rows; e += kSelBlock) {
+                const int k = rb0 * tile_rows + e;
+                ts.row[0][e] = (k < nlive) ? __ldg(rlist + k) : -1;
+                ts.val[0][e] = (k < nlive) ? __ldg(rval + k) : (real)0;
+            }
+        }
+        __syncthreads();
         int rec_pending = -1;   // thread 0: tile whose completion record is still to be written
         int cur_chunk = -1;
         real sreg[EPT];
         while (tile < ntiles) {
-            if (threadIdx.x == 0) sh.next_word = atomicAdd(&la->word, 1ull);
+            unsigned long long wnext = 0ull;
+            if (threadIdx.x == 0) wnext = atomicAdd(&la->word, 1ull);
             const int tmap = reverse ? (ntiles - 1 - tile) : tile;
             const int chunk = tmap % P.nchunks;
-            const int rb = tmap / P.nchunks;
             const int c = chunk * chunk_cols + tx * EPT;
-            if (c < P.ld) {
-                const int k0 = rb * tile_rows + ty;
-                real a[U];
-                int row[U];   // stored row of list entry k0 + u*rpp; -1: nothing to do
-                PackView<real, VB> v[U];
+            real a[U];
+            int row[U];   // stored row of list entry ty + u*rpp of this tile; -1: nothing to do
+            PackView<real, VB> v[U];
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int k = k0 + u * rpp;
-                    row[u] = -1;
-                    a[u] = (real)0;
-                    if (k < nlive) {
-                        const int r = __ldg(rlist + k);
-                        a[u] = __ldg(rval + k);
-                        if (r != skip_row) row[u] = r;
-                    }
-                }
+            for (int u = 0; u < U; ++u) {
+                const int r = ts.row[buf][ty + u * rpp];
+                a[u] = ts.val[buf][ty + u * rpp];
+                row[u] = (r == skip_row || c >= P.ld) ? -1 : r;
+            }
 #pragma unroll
-                for (int u = 0; u < U; ++u)
-                    if (row[u] >= 0) v[u].p = ld_pack<0>(reinterpret_cast<const Pack<VB>*>(P.T + (long long)row[u] * P.ld + c));
-                if (chunk != cur_chunk) {
-                    cur_chunk = chunk;
+            for (int u = 0; u < U; ++u)
+                if (row[u] >= 0) v[u].p = ld_pack<0>(reinterpret_cast<const Pack<VB>*>(P.T + (long long)row[u] * P.ld + c));
+            if (chunk != cur_chunk && c < P.ld) {
+                cur_chunk = chunk;
 #pragma unroll
-                    for (int e = 0; e < EPT; ++e) sreg[e] = __ldg(svec + c + e);
-                }
-                // the record of the previous tile goes out while this tile's loads are in flight
+                for (int e = 0; e < EPT; ++e) sreg[e] = __ldg(svec + c + e);
+            }
+            if (threadIdx.x < 32) {
+                // warp 0: the record of the previous tile goes out, the next tile's list entries come in
                 if (threadIdx.x == 0 && rec_pending >= 0) st_release_u32(P.tile_rec + rec_pending, seq);
-                const int he = skip_col - c;   // lane of a column published before this tile was claimed: held old
-#pragma unroll
-                for (int u = 0; u < U; ++u)
-                    if (row[u] >= 0) {
-#pragma unroll
-                        for (int e = 0; e < EPT; ++e) {
-                            const real se = (e == he) ? (real)0 : sreg[e];
-                            v[u].e[e] = fma_r(se, a[u], v[u].e[e]);
-                        }
-                        st_pack<0>(reinterpret_cast<Pack<VB>*>(P.T + (long long)row[u] * P.ld + c), v[u].p);
-                    }
-                if (lp >= c && lp < c + EPT) {
-                    // the thread that owns the pivot column overwrites its entries with a_pr / pivot (src/solver.cu:43)
-                    const real pv = (real)__ldcg(&cur->piv);
-#pragma unroll 1
-                    for (int u = 0; u < U; ++u) {
-                        const int k = k0 + u * rpp;
-                        if (k < nlive) {
-                            const int r = __ldg(rlist + k);
-                            if (r != skip_row) P.T[(long long)r * P.ld + lp] = div_r(__ldg(rval + k), pv);
-                        }
+                wnext = __shfl_sync(0xffffffffu, wnext, 0);
+                const int ntile = (int)(wnext & kTicketMask) + base;
+                if (threadIdx.x == 0) ts.word[buf ^ 1] = wnext;
+                if (ntile < ntiles) {
+                    const int ntmap = reverse ? (ntiles - 1 - ntile) : ntile;
+                    const int nrb = ntmap / P.nchunks;
+                    for (int e = threadIdx.x; e < tile_rows; e += 32) {
+                        const int k = nrb * tile_rows + e;
+                        ts.row[buf ^ 1][e] = (k < nlive) ? __ldg(rlist + k) : -1;
+                        ts.val[buf ^ 1][e] = (k < nlive) ? __ldg(rval + k) : (real)0;
                     }
                 }
-            } else if (threadIdx.x == 0 && rec_pending >= 0) {
-                st_release_u32(P.tile_rec + rec_pending, seq);
+            }
+            const int he = skip_col - c;   // lane of a column published before this tile was claimed: held old
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (row[u] >= 0) {
+#pragma unroll
+                    for (int e = 0; e < EPT; ++e) {
+                        const real se = (e == he) ? (real)0 : sreg[e];
+                        v[u].e[e] = fma_r(se, a[u], v[u].e[e]);
+                    }
+                    st_pack<0>(reinterpret_cast<Pack<VB>*>(P.T + (long long)row[u] * P.ld + c), v[u].p);
+                }
+            if (lp >= c && lp < c + EPT) {
+                // the thread that owns the pivot column overwrites its entries with a_pr / pivot (src/solver.cu:43)
+                const real pv = (real)__ldcg(&cur->piv);
+#pragma unroll 1
+                for (int u = 0; u < U; ++u) {
+                    const int r = ts.row[buf][ty + u * rpp];
+                    if (r >= 0 && r != skip_row) P.T[(long long)r * P.ld + lp] = div_r(ts.val[buf][ty + u * rpp], pv);
+                }
             }
             // tiles claimed after both publications are never waited for: no record needed
             rec_pending = (skip_col >= 0) ? -1 : tmap;
             __syncthreads();
-            const unsigned long long w = sh.next_word;
-            __syncthreads();
+            buf ^= 1;
+            const unsigned long long w = ts.word[buf];
             tile = (int)(w & kTicketMask) + base;
             skip_row = (int)((w >> kTicketBits) & kRowMask) - 1;
             skip_col = (int)(w >> kColShift) - 1;

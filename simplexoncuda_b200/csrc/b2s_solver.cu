@@ -152,7 +152,7 @@ struct SolverImpl final : SolverBase {
     real *col2 = nullptr, *s2 = nullptr, *rowp2 = nullptr, *rowval = nullptr;
     int *rowlist = nullptr, *rowpos = nullptr;
     int la_grid = 0;
-    int la_helpers = 8;
+    int la_helpers = 0;   // 0 = choose: 4 on one GPU, 8 when sharded (the chain then contains two NVLink round trips)
     long long wait_cycles = 4000000000ll;
     int fault_rank = -1;
     long long fault_pivot = 0;
@@ -590,8 +590,9 @@ struct SolverImpl final : SolverBase {
                     cudaMemsetAsync(tile_rec, 0, sizeof(unsigned) * cap_tiles, stream);
                 }
             }
-            la_grid = (int)std::max<long long>(1, std::min<long long>(num_sms, std::max<long long>(max_tiles + la_helpers, P.Gc)));
-            P.helpers = std::min(la_helpers, la_grid);
+            const int want = la_helpers > 0 ? la_helpers : (world > 1 ? 8 : 4);   // measured: profiles/r02_lookahead.md
+            la_grid = (int)std::max<long long>(1, std::min<long long>(num_sms, std::max<long long>(max_tiles + want, P.Gc)));
+            P.helpers = std::min(want, la_grid);
             P.la = la;
             P.tile_rec = tile_rec;
             P.col2 = col2;

@@ -24,16 +24,19 @@ def _ngpus():
         return 0
 
 
-@pytest.mark.parametrize("mode", ["p2p-launches", "p2p-persistent", "nccl"])
+@pytest.mark.parametrize("mode", ["p2p-lookahead", "p2p-launches", "p2p-persistent", "nccl"])
 @pytest.mark.parametrize("world", [2, 4, 8])
 def test_sharded_solves_match_oracle(world, mode):
-    """All three exchange implementations: peer-memory kernels (default), the persistent loop kernel with
-    peer-memory exchanges, and the NCCL fallback (B2S_P2P=0)."""
+    """All exchange implementations: the look-ahead kernel (default: both exchanges overlapped under the streaming update),
+    the four-launch peer-memory kernels, the persistent loop kernel with peer-memory exchanges, and the NCCL fallback
+    (B2S_P2P=0)."""
     if _ngpus() < world:
         pytest.skip(f"needs {world} GPUs")
-    if mode != "p2p-launches" and world > 2:
+    if mode != "p2p-lookahead" and world > 2:
         pytest.skip("alternative exchange paths are exercised at world size 2")
     env = dict(os.environ)
+    if mode == "p2p-launches":       # four launches per pivot, exchanges inside the ratio / gather kernels (round-1 path)
+        env["B2S_LOOKAHEAD"] = "0"
     if mode == "p2p-persistent":
         env["B2S_TEST_PERSISTENT"] = "1"
     if mode == "nccl":
