@@ -32,6 +32,7 @@ constexpr int kRuleBland = 2;
 constexpr int kSelBlock = 512;   // reference stage-1 block size (src/reduction.cu:6)
 constexpr int kMaxSlots = 1024;  // reference stage-1 grid cap  (src/reduction.cu:7)
 constexpr int kMaxPeers = 8;     // GPUs of one box
+constexpr int kLaMaxHelpers = 16;  // helper CTAs of the look-ahead chain (b2s_lookahead.cuh)
 
 // Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-stream-serialization
 // attribute may start while its predecessor drains; it must call pdl_wait() before touching anything the
@@ -275,6 +276,7 @@ struct PivotParams {
     long long rowp_stride;
     long long wait_cycles;  // bound of every device-side wait (clock64 ticks)
     int helpers;            // CTAs of the update kernel that run the look-ahead chain before they stream
+    int la_u;               // 256-bit loads each streaming thread keeps in flight (8, or 4: half the queueing delay for the chain)
     int fault_rank;         // fault injection (tests): this rank stops publishing from pivot fault_pivot on
     long long fault_pivot;
 };
@@ -295,6 +297,9 @@ struct ArenaHeader {
     unsigned long long flag_slots[2][kMaxPeers];
     unsigned long long flag_rowp[2];
     unsigned long long pad[6];
+    // look-ahead chain (b2s_lookahead.cuh): one flag per (rank, helper) / per owner helper, so nobody waits for a "last" CTA
+    unsigned long long la_flag_slots[2][kMaxPeers][kLaMaxHelpers];
+    unsigned long long la_flag_rowp[2][kLaMaxHelpers];
 };
 
 template <typename real>

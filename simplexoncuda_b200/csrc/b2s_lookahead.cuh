@@ -46,7 +46,6 @@
 
 namespace b2s {
 
-constexpr int kLaMaxHelpers = 16;
 constexpr int kStatusInternal = -97;  // the loop found no proposal for its pivot (cannot happen; surfaced as an error)
 
 // Ticket word layout.
@@ -55,7 +54,10 @@ constexpr int kRowBits = 19;                                      // published s
 constexpr unsigned long long kTicketMask = (1ull << kTicketBits) - 1ull;
 constexpr unsigned long long kRowMask = (1ull << kRowBits) - 1ull;
 constexpr int kColShift = kTicketBits + kRowBits;                 // published local column + 1 (<= 2^23)
-constexpr unsigned kNoColumn = 0x7fffffu;                         // "no column will be published during this pivot"
+constexpr unsigned kNoColumn = 0x7ffffeu;                         // "no column will be published during this pivot"
+constexpr unsigned long long kColMask = (1ull << 23) - 1ull;
+constexpr unsigned long long kQuietBit = 1ull << 63;              // the helpers are done classifying: stop writing tile records
+constexpr unsigned kRecHeld = 0x80000000u;                        // tile record: the claimer held the published column old
 
 // The complete selection of one pivot.  Two generations, indexed by the parity of the pivot number.
 struct Proposal {
@@ -69,8 +71,10 @@ struct Proposal {
     unsigned p_seq;   // == pivot number once p is valid (or status_next == kUnbounded)
     unsigned rowp_seq;   // one GPU: == pivot number once rowp' is complete (sharded: the arena's flag_rowp)
     unsigned ready_seq;  // == pivot number once everything is in place: the pivot may execute
-    unsigned row_pub_seq, col_pub_seq;  // publication hand-shake between the helpers
-    unsigned c_row, c_col;              // tiles claimed before the row / column publication
+    unsigned c_row;   // tiles claimed before the row publication
+    int rbq;          // row block of the running update's list that holds row 1+q' (-1: none)
+    double aq;        // rowp[1+q'] of the running pivot
+    unsigned pad1, pad2;
     long long nz;     // length of the row list: rows (other than row 0) the update of this pivot streams
 };
 
@@ -82,6 +86,8 @@ struct LaState {
     unsigned pad0;
     unsigned cnt_seq[kLaMaxHelpers];  // row-list compaction: helper h has published cnt[h] for pivot cnt_seq[h]
     int cnt[kLaMaxHelpers];
+    unsigned slot_seq[kLaMaxHelpers]; // one GPU: helper h has written its ratio-test block winners for pivot slot_seq[h]
+    unsigned done_seq[kLaMaxHelpers]; // helper h has finished the chain for pivot done_seq[h]
     unsigned long long stamps[8];  // %globaltimer at the chain's milestones of the last pivot (profiling)
 };
 
@@ -104,7 +110,7 @@ __device__ __forceinline__ unsigned long long globaltimer()
 }
 
 // Block-uniform bounded wait until *flag == want (thread 0 polls).  Returns false on timeout.
-__device__ __forceinline__ bool la_wait_u32(const unsigned* flag, unsigned want, long long cycles, int* s_ok)
+__device__ __noinline__ bool la_wait_u32(const unsigned* flag, unsigned want, long long cycles, int* s_ok)
 {
     if (threadIdx.x == 0) {
         const long long t0 = clock64();
@@ -122,7 +128,7 @@ __device__ __forceinline__ bool la_wait_u32(const unsigned* flag, unsigned want,
     __syncthreads();
     return ok;
 }
-__device__ __forceinline__ bool wait_flag_cycles(const unsigned long long* flag, unsigned long long seq, long long cycles)
+__device__ __noinline__ bool wait_flag_cycles(const unsigned long long* flag, unsigned long long seq, long long cycles)
 {
     const long long t0 = clock64();
     while (ld_acquire_sys(flag) < seq) {
@@ -136,6 +142,23 @@ template <typename real>
 __device__ __forceinline__ real* la_rowp(const PivotParams<real>& P, int par)
 {
     return P.world > 1 ? arena_rowp(P, P.rank, par) : P.rowp2 + (size_t)par * P.rowp_stride;
+}
+
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p)
+{
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// Per-thread bounded wait for a tile's completion record (pivot number, possibly with the held-column bit); returns it.
+__device__ __noinline__ unsigned la_poll_rec(const unsigned* rec, unsigned seq, long long cycles)
+{
+    const long long t0 = clock64();
+    unsigned v;
+    while (((v = ld_acquire_u32(rec)) & 0x7fffffffu) != seq) {
+        if (clock64() - t0 > cycles) break;
+    }
+    return v;
 }
 
 // Sweep position of tile (row block rb, column chunk) -- the inverse of the streaming loop's mapping.
@@ -155,6 +178,25 @@ struct LaTileSmem {
     real val[2][kLaMaxTileRows];
 };
 
+// Publications carried by a ticket word: row to leave alone, column to hold old (-1: none), and whether the tile's completion
+// record is still wanted.
+struct LaClaim {
+    int tile;       // ticket count (add the number of implicitly claimed tiles)
+    int skip_row;
+    int skip_col;
+    bool record;
+};
+__device__ __forceinline__ LaClaim la_decode(unsigned long long w)
+{
+    LaClaim c;
+    c.tile = (int)(w & kTicketMask);
+    c.skip_row = (int)((w >> kTicketBits) & kRowMask) - 1;
+    const unsigned col = (unsigned)((w >> kColShift) & kColMask);
+    c.skip_col = (col == 0u || col == kNoColumn) ? -1 : (int)col - 1;
+    c.record = !(w & kQuietBit) && col != kNoColumn;
+    return c;
+}
+
 struct LaShared {
     unsigned long long next_word;
     int ok;
@@ -164,17 +206,54 @@ struct LaShared {
 };
 
 // ---------------------------------------------------------------------------------------------
+// The chain runs once per pivot on a handful of SMs whose instruction caches are cold, while the memory system
+// is saturated by the streaming CTAs: every instruction-cache miss costs microseconds.  Its code is therefore
+// kept small -- divisions, tournament trees and the per-block ratio test are out-of-line functions shared by all
+// call sites instead of being inlined a dozen times (216 KB -> tens of KB of SASS; profiles/r02_lookahead.md).
+// ---------------------------------------------------------------------------------------------
+template <typename real>
+__device__ __noinline__ real la_div(real a, real b)
+{
+    return div_r(a, b);
+}
+template <typename real>
+__device__ __noinline__ void la_tree512(int rule, Cand<real>& c, TreeSmem<real>& sm)
+{
+    block_tree_512(rule, c, sm);
+}
+template <typename real>
+__device__ __noinline__ void la_stage2(int rule, const real* slot_v, const int* slot_i, const int* slot_k, int G, Cand<real>& w,
+                                       TreeSmem<real>& sm)
+{
+    if (G > 1) {
+        stage2_1024(rule, slot_v, slot_i, slot_k, G, w, sm);
+    } else {
+        w.v = __ldcg(slot_v);
+        w.i = __ldcg(slot_i);
+        w.k = __ldcg(slot_k);
+    }
+}
+template <typename real>
+__device__ __noinline__ real la_max512(real v, real* smax)
+{
+    return block_max_512(v, smax);
+}
+
+// ---------------------------------------------------------------------------------------------
 // Stage "cost": cost update of the running pivot (src/solver.cu:48-56) + entering tournament of the next
 // (src/reduction.cu:51-104 over costsVector+1).  Block b plays reference stage-1 block b; the CTA that
-// draws the last ticket plays stage 2 and publishes q' (or "optimal") into the next proposal.
+// draws the last ticket plays stage 2, publishes the entering variable's row into the ticket word (from then
+// on the streaming CTAs leave that row to the helpers) and releases q' (or "optimal") to the helpers.
+// Runs on the CTAs first_cta .. first_cta+ncta-1.
 // ---------------------------------------------------------------------------------------------
 template <typename real>
 __device__ __noinline__ void la_cost_blocks(const PivotParams<real>& P, LaState* la, Proposal* nxt, unsigned tseq,
-                                            const real* rowp, real sc, TreeSmem<real>& sm, LaShared& sh)
+                                            const real* rowp, real sc, int first_cta, int ncta, const int* posC, int tile_rows,
+                                            TreeSmem<real>& sm, LaShared& sh)
 {
     const long long Nc = P.Rc - 1;
     const int rule = P.rule;
-    for (int b = blockIdx.x; b < P.Gc; b += gridDim.x) {
+    for (int b = (int)blockIdx.x - first_cta; b < P.Gc; b += ncta) {
         Cand<real> c;
         c.v = Limits<real>::big();
         c.i = -1;
@@ -191,7 +270,7 @@ __device__ __noinline__ void la_cost_blocks(const PivotParams<real>& P, LaState*
             if (beats(rule, o, c)) c = o;
         }
         if (b == 0 && threadIdx.x == 0) P.cost[0] = fma_r(sc, __ldg(rowp), P.cost[0]);  // objective value
-        block_tree_512(rule, c, sm);
+        la_tree512(rule, c, sm);
         if (threadIdx.x == 0) {
             P.cslot_v[b] = c.v;
             P.cslot_i[b] = c.i;
@@ -206,16 +285,26 @@ __device__ __noinline__ void la_cost_blocks(const PivotParams<real>& P, LaState*
         if (last) {
             __threadfence();
             Cand<real> w;
-            if (P.Gc > 1)
-                stage2_1024(rule, P.cslot_v, P.cslot_i, P.cslot_k, P.Gc, w, sm);
-            else
-                w = c;
+            la_stage2(rule, P.cslot_v, P.cslot_i, P.cslot_k, P.Gc, w, sm);   // (one block: its own winner, just written)
             if (threadIdx.x == 0) {
+                const bool go = w.i >= 0 && cmp3((double)w.v, 0.0) < 0;   // src/solver.cu:87-88
                 nxt->q = w.i;
                 nxt->cq = (double)w.v;
-                nxt->status_next = (w.i >= 0 && cmp3((double)w.v, 0.0) < 0) ? kRunning : kFeasible;  // src/solver.cu:87-88
+                nxt->status_next = go ? kRunning : kFeasible;
+                if (go) {
+                    // publish the entering variable's row: tiles claimed from now on leave it to the helpers.  Its position in
+                    // the running list and its pivot-constraint entry travel with q', so the helpers need no further lookup.
+                    const long long rq = stored_row(P, 1 + (long long)w.i);
+                    const int posq = __ldg(posC + rq);
+                    const real aq = __ldg(rowp + rq);
+                    const unsigned long long old = atomicAdd(&la->word, (unsigned long long)(rq + 1) << kTicketBits);
+                    nxt->c_row = (unsigned)(old & kTicketMask);
+                    nxt->rbq = posq >= 0 ? posq / tile_rows : -1;
+                    nxt->aq = (double)aq;
+                } else {
+                    atomicAdd(&la->word, (unsigned long long)kNoColumn << kColShift);   // phase over: no column will follow
+                }
                 la->ticket_cost = 0;
-                __threadfence();
                 st_release_u32(&nxt->q_seq, tseq);
             }
         }
@@ -231,15 +320,35 @@ __device__ __forceinline__ void la_ratio_stage2(const PivotParams<real>& P, cons
 {
     mx = Limits<real>::tiny();
     for (int b = threadIdx.x; b < P.Gm; b += kSelBlock) mx = fmax(mx, __ldcg(slot_max + b));
-    mx = block_max_512(mx, smax);
+    mx = la_max512(mx, smax);
     const int tree_rule = (P.rule == kRuleReference) ? kRuleReference : kRuleLowest;
-    if (P.Gm > 1) {
-        stage2_1024(tree_rule, slot_v, slot_i, slot_k, P.Gm, w, sm);
-    } else {
-        w.v = __ldcg(slot_v);
-        w.i = __ldcg(slot_i);
-        w.k = __ldcg(slot_k);
+    la_stage2(tree_rule, slot_v, slot_i, slot_k, P.Gm, w, sm);
+}
+
+// One reference stage-1 block of the ratio test (src/reduction.cu:106-140) on values already in registers: entering
+// column entry a (after the running update), RHS entry bb.  Writes col'[li]; block winner and block max valid in thread 0.
+template <typename real>
+__device__ __noinline__ void la_ratio_block(const PivotParams<real>& P, real a, real bb, long long li, int bvar, real* colN,
+                                            Cand<real>& c, real& mx, TreeSmem<real>& sm, real* smax)
+{
+    const int rule = P.rule;
+    const int tree_rule = (rule == kRuleReference) ? kRuleReference : kRuleLowest;
+    c.v = Limits<real>::big();
+    c.i = -1;
+    c.k = -1;
+    mx = Limits<real>::tiny();
+    if (li < P.m_loc) {
+        colN[li] = a;
+        mx = fmax(mx, a);   // src/reduction.cu:143-184, identity DBL_MIN
+        const long long gi = P.col0 + li;
+        Cand<real> o;
+        o.v = (cmp3((double)a, 0.0) > 0) ? div_r(bb, a) : Limits<real>::big();   // src/reduction.cu:106-114
+        o.i = (int)gi;
+        o.k = (rule == kRuleBland) ? ((o.v < Limits<real>::big()) ? bvar : -1) : (int)gi;
+        if (beats(tree_rule, o, c)) c = o;
     }
+    mx = block_max_512(mx, smax);
+    block_tree_512(tree_rule, c, sm);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -247,19 +356,48 @@ __device__ __forceinline__ void la_ratio_stage2(const PivotParams<real>& P, cons
 // q, p, piv; vectors svec / rowp and the row list of the running update) and builds the proposal of pivot
 // seq+1 while the other CTAs stream.  LIVE = false: the tableau is quiescent (prologue kernel: first pivot of
 // a phase or of an iterate() call); q' comes from the select kernel (st->q / st->cq), every element is final.
+//
+// The memory system is saturated by the streaming CTAs while this runs, so a dependent global access costs
+// 2-3 us (measured: profiles/r02_la_stage_profile_v1_*.jsonl).  Every stage therefore issues all of its loads
+// at once (batches of kLaRB per thread) and the stages hand over through as few flags as possible.
 // ---------------------------------------------------------------------------------------------
+constexpr int kLaBB = 2;   // ratio-test blocks per batch and helper
+constexpr int kLaRB = 4;   // pivot-constraint rows per batch and thread
+
+// Bounded wait until the `count` flags flags[0 .. count) (stride in elements) all equal `want`; thread i polls flag i.
+__device__ __noinline__ bool la_wait_many_u32(const unsigned* flags, int count, unsigned want, long long cycles)
+{
+    int ok = 1;
+    if ((int)threadIdx.x < count) {
+        const long long t0 = clock64();
+        while (ld_acquire_u32(flags + threadIdx.x) != want) {
+            if (clock64() - t0 > cycles) {
+                ok = 0;
+                break;
+            }
+        }
+    }
+    return __syncthreads_and(ok) != 0;
+}
+__device__ __noinline__ bool la_wait_many_sys(const unsigned long long* flags, int count, unsigned long long want, long long cycles)
+{
+    int ok = 1;
+    if ((int)threadIdx.x < count) ok = wait_flag_cycles(flags + threadIdx.x, want, cycles) ? 1 : 0;
+    return __syncthreads_and(ok) != 0;
+}
+
 template <typename real, bool LIVE>
 __device__ __noinline__ void la_chain(const PivotParams<real>& P, LaState* la, unsigned seq, int h, int H,
                                       const real* rowp, const real* svec, real piv, long long lp, int p_cur, int q_cur,
                                       bool reverse, long long ntiles, TreeSmem<real>& sm, real* smax, LaShared& sh)
 {
+    __shared__ int s_scan[kLaRB][kSelBlock / 32];
     DevState* st = P.st;
     const unsigned tseq = seq + 1u;     // the pivot this chain prepares
     const int par = (int)(seq & 1u), tpar = par ^ 1;
     Proposal* nxt = &la->prop[tpar];
     const bool sharded = P.world > 1;
     const int rule = P.rule;
-    const int tree_rule = (rule == kRuleReference) ? kRuleReference : kRuleLowest;
     const long long cyc = P.wait_cycles;
     const long long base = (long long)gridDim.x - H;   // tiles claimed implicitly at launch (LIVE only)
     real* colN = P.col2 + (size_t)tpar * P.ld;
@@ -267,28 +405,58 @@ __device__ __noinline__ void la_chain(const PivotParams<real>& P, LaState* la, u
     real* rowpN = la_rowp(P, tpar);
     const int* posC = P.rowpos + (size_t)par * P.rowp_stride;   // row -> position in the running update's row list
     const int rpp = kSelBlock >> P.log2_tpr;
-    const long long tile_rows = (long long)rpp * 8;
+    const long long tile_rows = (long long)rpp * P.la_u;
     const long long chunk_cols = (long long)(32 / (int)sizeof(real)) << P.log2_tpr;
     const real a0 = LIVE ? __ldg(rowp) : (real)0;   // rowp[0] = b_p of the running pivot
     const bool own_cur = LIVE && lp >= 0 && lp < P.m_loc;
+    // Helper h owns the contiguous slice [r_lo, r_hi) of stored rows for the pivot-constraint gather and the row list.
+    const long long slice = (((P.Rs + H - 1) / H) + kSelBlock - 1) / kSelBlock * kSelBlock;
+    const long long r_lo = (long long)h * slice, r_hi = (r_lo + slice < P.Rs) ? r_lo + slice : P.Rs;
+    const int nchunk = r_hi > r_lo ? (int)((r_hi - r_lo + kSelBlock - 1) / kSelBlock) : 0;
+    const int nbatch = (nchunk + kLaRB - 1) / kLaRB;
+    // what the gather will need from the running update for the first batch of its slice: fetched now, used much later
+    int pos0[kLaRB];
+    real ak0[kLaRB];
+#pragma unroll
+    for (int k = 0; k < kLaRB; ++k) {
+        const long long r = r_lo + (long long)k * kSelBlock + threadIdx.x;
+        pos0[k] = (LIVE && r < r_hi) ? __ldg(posC + r) : -2;
+        ak0[k] = (LIVE && r < r_hi) ? __ldg(rowp + r) : (real)0;
+    }
 
     if (LIVE) {
         // ---- stage 0: row 0 (RHS) of the running update -- it is not in the row list ---------------------------
-        for (int bl = h; bl < P.Gm_loc; bl += H) {
-            const long long li = (long long)bl * kSelBlock + threadIdx.x;
-            if (li < P.m_loc) {
-                const real x = __ldcg(P.T + li);
-                P.T[li] = (li == lp) ? div_r(a0, piv) : fma_r(__ldg(svec + li), a0, x);
+        for (int bl0 = h; bl0 < P.Gm_loc; bl0 += H * kLaBB) {
+            real x[kLaBB], sv[kLaBB];
+#pragma unroll
+            for (int k = 0; k < kLaBB; ++k) {
+                const long long li = (long long)(bl0 + k * H) * kSelBlock + threadIdx.x;
+                const bool ok = bl0 + k * H < P.Gm_loc && li < P.m_loc;
+                x[k] = ok ? __ldcg(P.T + li) : (real)0;
+                sv[k] = ok ? __ldg(svec + li) : (real)0;
+            }
+#pragma unroll
+            for (int k = 0; k < kLaBB; ++k) {
+                const long long li = (long long)(bl0 + k * H) * kSelBlock + threadIdx.x;
+                if (bl0 + k * H < P.Gm_loc && li < P.m_loc) P.T[li] = (li == lp) ? la_div(a0, piv) : fma_r(sv[k], a0, x[k]);
             }
         }
         // rows the list leaves out (a_pr == 0) are unchanged by this update, pivot column included: a_pr / pivot = a_pr.
         // The tableau may still hold a held-old value there (see the header): write the true entry.
         if (own_cur && P.skip_zero) {
-            for (long long r = (long long)h * kSelBlock + threadIdx.x; r < P.Rs; r += (long long)H * kSelBlock)
-                if (r != 0 && __ldg(posC + r) < 0) P.T[r * P.ld + lp] = __ldg(rowp + r);
+            for (int bt = 0; bt < nbatch; ++bt) {
+#pragma unroll
+                for (int k = 0; k < kLaRB; ++k) {
+                    const long long r = r_lo + ((long long)bt * kLaRB + k) * kSelBlock + threadIdx.x;
+                    if (r < r_hi && r != 0) {
+                        const int pos = bt == 0 ? pos0[k] : __ldg(posC + r);
+                        if (pos < 0) P.T[r * P.ld + lp] = bt == 0 ? ak0[k] : __ldg(rowp + r);
+                    }
+                }
+            }
         }
         if (h == 0 && threadIdx.x == 0) la->stamps[1] = globaltimer();
-        // ---- stage Q: the entering variable of the next pivot ------------------------------------------------
+        // ---- stage Q: the entering variable of the next pivot (the cost CTAs have published its row already) ----
         if (!la_wait_u32(&nxt->q_seq, tseq, cyc, &sh.ok)) {
             if (h == 0 && threadIdx.x == 0) {
                 nxt->status_next = kStatusPeerTimeout;
@@ -296,252 +464,179 @@ __device__ __noinline__ void la_chain(const PivotParams<real>& P, LaState* la, u
             }
             return;
         }
-        __threadfence();
-        if (__ldcg(&nxt->status_next) != kRunning) {   // optimal after this pivot: nothing to prepare
-            if (h == 0 && threadIdx.x == 0) atomicAdd(&la->word, (unsigned long long)kNoColumn << kColShift);
-            return;
-        }
     } else if (h == 0 && threadIdx.x == 0) {
         nxt->q = __ldcg(&st->q);
         nxt->cq = __ldcg(&st->cq);
         nxt->status_next = kRunning;
     }
+    // everything the cost CTAs left for us, fetched in one go
+    const int sn = LIVE ? __ldcg(&nxt->status_next) : kRunning;
     const int qn = LIVE ? __ldcg(&nxt->q) : __ldcg(&st->q);
     const real cqn = (real)(LIVE ? __ldcg(&nxt->cq) : __ldcg(&st->cq));
+    const long long c_row = LIVE ? (long long)__ldcg(&nxt->c_row) : 0;
+    const long long rbq = LIVE ? (long long)__ldcg(&nxt->rbq) : -1;   // -1: no tile of the running update touches row 1+q'
+    const real aq = LIVE ? (real)__ldcg(&nxt->aq) : (real)0;          // rowp[1+q'] of the running pivot
+    if (sn != kRunning) return;   // optimal after this pivot: nothing to prepare
     const long long rq = stored_row(P, 1 + (long long)qn);
     if (h == 0 && threadIdx.x == 0) la->stamps[2] = globaltimer();
 
     // ---- stage R: entering column + RHS after the running update, ratio-test stage 1 ----------------------
-    long long c_row = 0;
-    long long rbq = -1;   // row block (of the running update's list) that holds row rq; -1: no tile touches it
-    if (LIVE) {
-        if (h == 0 && threadIdx.x == 0) {
-            const unsigned long long old = atomicAdd(&la->word, (unsigned long long)(rq + 1) << kTicketBits);
-            nxt->c_row = (unsigned)(old & kTicketMask);
-            __threadfence();
-            st_release_u32(&nxt->row_pub_seq, tseq);
-        }
-        if (!la_wait_u32(&nxt->row_pub_seq, tseq, cyc, &sh.ok)) return;
-        c_row = (long long)__ldcg(&nxt->c_row);
-        const int posq = __ldg(posC + rq);
-        if (posq >= 0) rbq = posq / tile_rows;
-    }
-    const real aq = LIVE ? __ldg(rowp + rq) : (real)0;   // rowp[1+q'] of the running pivot
-    for (int bl = h; bl < P.Gm_loc; bl += H) {
-        const int gb = P.Gm_loc0 + bl;
-        const long long li = (long long)bl * kSelBlock + threadIdx.x;
-        bool old_vals = false;
-        if (LIVE) {
-            old_vals = true;
-            if (rbq >= 0) {
-                const int chunk = (int)(((long long)bl * kSelBlock) / chunk_cols);
-                const long long tmap = rbq * P.nchunks + chunk;
-                const long long t = reverse ? (ntiles - 1 - tmap) : tmap;
-                old_vals = t >= c_row + base;  // claimed after the publication: the claimer leaves row rq alone
-                if (!old_vals) {               // claimed before: wait until that tile is complete, then read the new values
-                    if (!la_wait_u32(P.tile_rec + tmap, seq, cyc, &sh.ok)) {
-                        if (threadIdx.x == 0) nxt->status_next = kStatusPeerTimeout;
-                        return;
+    for (int bl0 = h; bl0 < P.Gm_loc; bl0 += H * kLaBB) {
+        bool old_vals[kLaBB];
+        real av[kLaBB], bv[kLaBB], sv[kLaBB];
+#pragma unroll
+        for (int k = 0; k < kLaBB; ++k) {
+            const int bl = bl0 + k * H;
+            old_vals[k] = false;
+            if (LIVE && bl < P.Gm_loc) {
+                old_vals[k] = true;
+                if (rbq >= 0) {
+                    const int chunk = (int)(((long long)bl * kSelBlock) / chunk_cols);
+                    const long long tmap = rbq * P.nchunks + chunk;
+                    const long long t = reverse ? (ntiles - 1 - tmap) : tmap;
+                    old_vals[k] = t >= c_row + base;  // claimed after the publication: the claimer leaves row rq alone
+                    if (!old_vals[k]) {               // claimed before: wait until that tile is complete, then read the new values
+                        if (!la_wait_u32(P.tile_rec + tmap, seq, cyc, &sh.ok)) {
+                            if (threadIdx.x == 0) nxt->status_next = kStatusPeerTimeout;
+                            return;
+                        }
                     }
                 }
             }
         }
-        Cand<real> c;
-        c.v = Limits<real>::big();
-        c.i = -1;
-        c.k = -1;
-        real mx = Limits<real>::tiny();
-        if (li < P.m_loc) {
-            real* e = P.T + rq * P.ld + li;
-            real a = __ldcg(e);
-            if (old_vals) {
-                a = (li == lp) ? div_r(aq, piv) : fma_r(__ldg(svec + li), aq, a);
-                *e = a;
-            }
-            const real bb = __ldcg(P.T + li);
-            colN[li] = a;
-            mx = fmax(mx, a);   // src/reduction.cu:143-184, identity DBL_MIN
-            const long long gi = P.col0 + li;
-            Cand<real> o;
-            o.v = (cmp3((double)a, 0.0) > 0) ? div_r(bb, a) : Limits<real>::big();   // src/reduction.cu:106-114
-            o.i = (int)gi;
-            if (rule == kRuleBland) {
-                const int bv = (LIVE && gi == p_cur) ? q_cur : P.base[gi];   // base[p] = q of the running pivot is committed at its end
-                o.k = (o.v < Limits<real>::big()) ? bv : -1;
-            } else {
-                o.k = (int)gi;
-            }
-            if (beats(tree_rule, o, c)) c = o;
+#pragma unroll
+        for (int k = 0; k < kLaBB; ++k) {
+            const long long li = (long long)(bl0 + k * H) * kSelBlock + threadIdx.x;
+            const bool ok = bl0 + k * H < P.Gm_loc && li < P.m_loc;
+            av[k] = ok ? __ldcg(P.T + rq * P.ld + li) : (real)0;
+            bv[k] = ok ? __ldcg(P.T + li) : (real)0;
+            sv[k] = (ok && old_vals[k]) ? __ldg(svec + li) : (real)0;
         }
-        mx = block_max_512(mx, smax);
-        block_tree_512(tree_rule, c, sm);
-        if (!sharded) {
-            if (threadIdx.x == 0) {
-                P.rslot_v[gb] = c.v;
-                P.rslot_max[gb] = mx;
-                P.rslot_i[gb] = c.i;
-                P.rslot_k[gb] = c.k;
+#pragma unroll
+        for (int k = 0; k < kLaBB; ++k) {   // (unrolled: av/bv/sv live in registers; the body is a call)
+            const int bl = bl0 + k * H;
+            if (bl >= P.Gm_loc) break;
+            const int gb = P.Gm_loc0 + bl;
+            const long long li = (long long)bl * kSelBlock + threadIdx.x;
+            real a = av[k];
+            int bvar = -1;
+            if (li < P.m_loc) {
+                if (old_vals[k]) {
+                    a = (li == lp) ? la_div(aq, piv) : fma_r(sv[k], aq, a);
+                    P.T[rq * P.ld + li] = a;
+                }
+                if (rule == kRuleBland) {
+                    const long long gi = P.col0 + li;
+                    bvar = (LIVE && gi == p_cur) ? q_cur : P.base[gi];   // base[p] = q of the running pivot is committed at its end
+                }
             }
-        } else {
-            if (threadIdx.x == 0) {
-                sh.d0 = (double)c.v;
-                sh.d1 = (double)mx;
-                sh.i0 = c.i;
-                sh.i1 = c.k;
+            Cand<real> c;
+            real mx;
+            la_ratio_block(P, a, bv[k], li, bvar, colN, c, mx, sm, smax);
+            if (!sharded) {
+                if (threadIdx.x == 0) {
+                    P.rslot_v[gb] = c.v;
+                    P.rslot_max[gb] = mx;
+                    P.rslot_i[gb] = c.i;
+                    P.rslot_k[gb] = c.k;
+                }
+            } else {
+                if (threadIdx.x == 0) {
+                    sh.d0 = (double)c.v;
+                    sh.d1 = (double)mx;
+                    sh.i0 = c.i;
+                    sh.i1 = c.k;
+                }
+                __syncthreads();
+                if (threadIdx.x < P.world) {
+                    ArenaHeader<real>* a2 = arena_of(P, threadIdx.x);
+                    a2->slot_v[tpar][gb] = (real)sh.d0;
+                    a2->slot_max[tpar][gb] = (real)sh.d1;
+                    a2->slot_i[tpar][gb] = sh.i0;
+                    a2->slot_k[tpar][gb] = sh.i1;
+                }
             }
             __syncthreads();
-            if (threadIdx.x < P.world) {
-                ArenaHeader<real>* a = arena_of(P, threadIdx.x);
-                a->slot_v[tpar][gb] = (real)sh.d0;
-                a->slot_max[tpar][gb] = (real)sh.d1;
-                a->slot_i[tpar][gb] = sh.i0;
-                a->slot_k[tpar][gb] = sh.i1;
-                __threadfence_system();
-            }
         }
-        __syncthreads();
     }
+    // My block winners are out: raise my flag (everywhere, when sharded), wait for every helper's (of every rank), then
+    // EVERY helper replays stage 2 itself -- no "last CTA", no second hand-over.
+    const real *slot_v = P.rslot_v, *slot_max = P.rslot_max;
+    const int *slot_i = P.rslot_i, *slot_k = P.rslot_k;
+    bool ok_x = true;
+    if (!sharded) {
+        if (threadIdx.x == 0) st_release_u32(&la->slot_seq[h], tseq);
+        ok_x = la_wait_many_u32(la->slot_seq, H, tseq, cyc);
+    } else {
+        const bool mute = P.fault_rank == P.rank && (long long)tseq >= P.fault_pivot;   // fault injection (tests)
+        // (thread r wrote this helper's winners into rank r's arena itself: its release store orders them, no extra fence)
+        if (threadIdx.x < P.world && !mute)
+            st_release_sys(&arena_of(P, threadIdx.x)->la_flag_slots[tpar][P.rank][h], (unsigned long long)tseq);
+        // flags of rank r, helper k: la_flag_slots[tpar][r][k]; ranks >= world never publish, so poll rank by rank
+        const ArenaHeader<real>* mine = arena_of(P, P.rank);
+        int okk = 1;
+        if ((int)threadIdx.x < P.world * H) {
+            const int r = threadIdx.x / H, k = threadIdx.x % H;
+            okk = wait_flag_cycles(&mine->la_flag_slots[tpar][r][k], (unsigned long long)tseq, cyc) ? 1 : 0;
+        }
+        ok_x = __syncthreads_and(okk) != 0;
+        slot_v = mine->slot_v[tpar];
+        slot_max = mine->slot_max[tpar];
+        slot_i = mine->slot_i[tpar];
+        slot_k = mine->slot_k[tpar];
+    }
+    Cand<real> w;
+    w.v = Limits<real>::big();
+    w.i = -1;
+    w.k = -1;
+    real mxall = Limits<real>::tiny();
+    if (ok_x) la_ratio_stage2(P, slot_v, slot_i, slot_k, slot_max, sm, smax, w, mxall);
     if (threadIdx.x == 0) {
-        if (sharded) __threadfence_system(); else __threadfence();
-        const unsigned t = atomicAdd(&la->ticket_ratio, 1u);
-        sh.flag = (t == (unsigned)H - 1u);
-    }
-    __syncthreads();
-    const bool last_ratio = sh.flag != 0;
-    __syncthreads();
-    if (last_ratio) {
-        __threadfence();
-        const real *slot_v = P.rslot_v, *slot_max = P.rslot_max;
-        const int *slot_i = P.rslot_i, *slot_k = P.rslot_k;
-        bool ok = true;
-        if (sharded) {
-            // all local winners are out: raise our flag everywhere, then wait for everybody's (local polling)
-            __threadfence_system();
-            const bool mute = P.fault_rank == P.rank && (long long)tseq >= P.fault_pivot;   // fault injection (tests)
-            if (threadIdx.x < P.world && !mute)
-                st_release_sys(&arena_of(P, threadIdx.x)->flag_slots[tpar][P.rank], (unsigned long long)tseq);
-            int okk = 1;
-            if (threadIdx.x < P.world)
-                okk = wait_flag_cycles(&arena_of(P, P.rank)->flag_slots[tpar][threadIdx.x], (unsigned long long)tseq, cyc) ? 1 : 0;
-            ok = __syncthreads_and(okk) != 0;
-            __threadfence_system();
-            const ArenaHeader<real>* mine = arena_of(P, P.rank);
-            slot_v = mine->slot_v[tpar];
-            slot_max = mine->slot_max[tpar];
-            slot_i = mine->slot_i[tpar];
-            slot_k = mine->slot_k[tpar];
-        }
-        Cand<real> w;
-        w.v = Limits<real>::big();
-        w.i = -1;
-        w.k = -1;
-        real mx = Limits<real>::tiny();
-        if (ok) la_ratio_stage2(P, slot_v, slot_i, slot_k, slot_max, sm, smax, w, mx);
-        if (threadIdx.x == 0) {
-            la->ticket_ratio = 0;
-            if (!ok) {
-                nxt->status_next = kStatusPeerTimeout;
-                nxt->p = -1;
-            } else if (cmp3((double)mx, 0.0) <= 0 || w.i < 0) {
-                nxt->status_next = kUnbounded;   // src/solver.cu:98-99
-                nxt->p = -1;
-            } else {
-                nxt->p = w.i;
-            }
-            __threadfence();
-            st_release_u32(&nxt->p_seq, tseq);
+        int pnn = -1, snn = kRunning;
+        if (!ok_x)
+            snn = kStatusPeerTimeout;
+        else if (cmp3((double)mxall, 0.0) <= 0 || w.i < 0)
+            snn = kUnbounded;   // src/solver.cu:98-99
+        else
+            pnn = w.i;
+        sh.i0 = pnn;
+        if (h == 0) {
+            nxt->p = pnn;
+            if (snn != kRunning) nxt->status_next = snn;
         }
     }
-    // ---- stage G: the owner of constraint p' gathers the raw pivot constraint after the running update ----
-    if (!la_wait_u32(&nxt->p_seq, tseq, cyc, &sh.ok)) return;
-    __threadfence();
+    __syncthreads();
+    const int pn = sh.i0;
+    __syncthreads();
     if (h == 0 && threadIdx.x == 0) la->stamps[3] = globaltimer();
-    const int pn = __ldcg(&nxt->p);
-    if (pn < 0) {   // unbounded (or a peer went silent): the phase ends instead of pivot tseq
-        if (LIVE && h == 0 && threadIdx.x == 0) atomicAdd(&la->word, (unsigned long long)kNoColumn << kColShift);
-        return;
-    }
     const long long lpn = (long long)pn - P.col0;
-    const bool owner = lpn >= 0 && lpn < P.m_loc;
+    const bool owner = pn >= 0 && lpn >= 0 && lpn < P.m_loc;
     const bool same_col = LIVE && owner && lpn == lp;   // the same constraint leaves twice in a row
     long long c_col = 0;
     if (LIVE) {
-        if (h == 0 && threadIdx.x == 0) {
-            const unsigned long long field = (owner && !same_col) ? (unsigned long long)(lpn + 1) : (unsigned long long)kNoColumn;
-            const unsigned long long old = atomicAdd(&la->word, field << kColShift);
-            nxt->c_col = (unsigned)(old & kTicketMask);
-            __threadfence();
-            st_release_u32(&nxt->col_pub_seq, tseq);
-        }
-        if (owner && !same_col) {
-            if (!la_wait_u32(&nxt->col_pub_seq, tseq, cyc, &sh.ok)) return;
-            c_col = (long long)__ldcg(&nxt->c_col);
-        }
-    }
-    if (owner) {
-        const int chunk = (int)(lpn / chunk_cols);
-        const real sp = (LIVE && !same_col) ? __ldg(svec + lpn) : (real)0;
-        int bad = 0;
-        for (long long r = (long long)h * kSelBlock + threadIdx.x; r < P.Rs; r += (long long)H * kSelBlock) {
-            real v;
-            if (same_col) {
-                v = div_r(__ldg(rowp + r), piv);   // T'[r][p] = a_pr / pivot (src/solver.cu:43)
-            } else {
-                const real* e = P.T + r * P.ld + lpn;
-                const int pos = (LIVE && r != 0 && r != rq) ? __ldg(posC + r) : -2;
-                if (pos >= 0) {
-                    const long long tmap = (pos / tile_rows) * P.nchunks + chunk;
-                    const long long t = reverse ? (ntiles - 1 - tmap) : tmap;
-                    if (t >= c_col + base) {
-                        v = fma_r(sp, __ldg(rowp + r), __ldcg(e));   // held old by its claimer: apply the running update here
-                    } else {
-                        const unsigned* rec = P.tile_rec + tmap;
-                        const long long t0 = clock64();
-                        while (ld_acquire_u32(rec) != seq) {
-                            if (clock64() - t0 > cyc) {
-                                bad = 1;
-                                break;
-                            }
-                        }
-                        v = __ldcg(e);   // updated in full by a tile claimed before the publication
-                    }
-                } else if (pos == -1) {
-                    v = fma_r(sp, __ldg(rowp + r), __ldcg(e));       // not in the list (a_pr == 0): no tile touches it
-                } else {
-                    v = __ldcg(e);       // rows 0 and 1+q' were finished by stages 0 / R; quiescent tableau: final
-                }
-            }
-            if (!sharded) {
-                rowpN[r] = v;
-            } else {
-                for (int w = 0; w < P.world; ++w) arena_rowp(P, w, tpar)[r] = v;
-            }
-        }
-        bad = __syncthreads_or(bad);
+        // Publish the next pivot column (its owner rank only, and not when the same constraint leaves twice in a row): tiles
+        // claimed from now on hold that column old.  Every helper ORs the same field in and keeps the ticket count ITS atomic
+        // returned: tiles at or beyond that count certainly saw the column; earlier ones say in their record what they did.
         if (threadIdx.x == 0) {
-            if (bad) nxt->status_next = kStatusPeerTimeout;
-            if (sharded) __threadfence_system(); else __threadfence();
-            const unsigned t = atomicAdd(&la->ticket_gather, 1u);
-            sh.flag = (t == (unsigned)H - 1u);
+            const unsigned long long field = (owner && !same_col) ? (unsigned long long)(lpn + 1) : (unsigned long long)kNoColumn;
+            const unsigned long long old = atomicOr(&la->word, field << kColShift);
+            sh.next_word = old & kTicketMask;
         }
         __syncthreads();
-        const bool last_g = sh.flag != 0;
+        c_col = (long long)sh.next_word;
         __syncthreads();
-        if (last_g) {
-            if (sharded) {
-                __threadfence_system();
-                if (threadIdx.x < P.world) st_release_sys(&arena_of(P, threadIdx.x)->flag_rowp[tpar], (unsigned long long)tseq);
-            }
-            if (threadIdx.x == 0) {
-                la->ticket_gather = 0;
-                __threadfence();
-                st_release_u32(&nxt->rowp_seq, tseq);
-            }
-        }
     }
-    // ---- stage S: s' = -col'/pivot' for the local slab, sc', and the row list of the next update -----------
-    if (sharded) {
-        if (threadIdx.x == 0) sh.ok = wait_flag_cycles(&arena_of(P, P.rank)->flag_rowp[tpar], (unsigned long long)tseq, cyc) ? 1 : 0;
+    if (pn < 0) return;   // unbounded (or a peer went silent): the phase ends instead of pivot tseq
+
+    // ---- stage G: the owner of constraint p' gathers the raw pivot constraint after the running update ----
+    const bool skip = P.skip_zero != 0;
+    real v0[kLaRB];   // values of the first batch stay in registers for the list pass
+#pragma unroll
+    for (int k = 0; k < kLaRB; ++k) v0[k] = (real)0;
+    int mine_cnt = 0;
+    if (!owner) {   // sharded, another rank owns p': wait for its helper h, which delivers exactly my slice
+        if (threadIdx.x == 0)
+            sh.ok = wait_flag_cycles(&arena_of(P, P.rank)->la_flag_rowp[tpar][h], (unsigned long long)tseq, cyc) ? 1 : 0;
         __syncthreads();
         const bool ok = sh.ok != 0;
         __syncthreads();
@@ -549,112 +644,245 @@ __device__ __noinline__ void la_chain(const PivotParams<real>& P, LaState* la, u
             if (h == 0 && threadIdx.x == 0) nxt->status_next = kStatusPeerTimeout;
             return;
         }
-        __threadfence_system();
-    } else {
-        if (!la_wait_u32(&nxt->rowp_seq, tseq, cyc, &sh.ok)) return;
-        __threadfence();
+    }
+    {
+        const int chunk = owner ? (int)(lpn / chunk_cols) : 0;
+        const real sp = (LIVE && owner && !same_col) ? __ldg(svec + lpn) : (real)0;
+        int bad = 0;
+        for (int bt = 0; bt < nbatch; ++bt) {
+            real v[kLaRB];
+            const long long rb0 = r_lo + (long long)bt * kLaRB * kSelBlock + threadIdx.x;
+            if (!owner) {
+#pragma unroll
+                for (int k = 0; k < kLaRB; ++k) {
+                    const long long r = rb0 + (long long)k * kSelBlock;
+                    v[k] = (r < r_hi) ? __ldcg(rowpN + r) : (real)0;
+                }
+            } else if (same_col) {
+#pragma unroll
+                for (int k = 0; k < kLaRB; ++k) {
+                    const long long r = rb0 + (long long)k * kSelBlock;
+                    v[k] = (r < r_hi) ? la_div(bt == 0 ? ak0[k] : __ldg(rowp + r), piv) : (real)0;   // T'[r][p] = a_pr / pivot (src/solver.cu:43)
+                }
+            } else {
+                int pos[kLaRB];
+                real ak[kLaRB];
+                unsigned rec[kLaRB];
+#pragma unroll
+                for (int k = 0; k < kLaRB; ++k) {
+                    const long long r = rb0 + (long long)k * kSelBlock;
+                    pos[k] = bt == 0 ? pos0[k] : ((LIVE && r < r_hi) ? __ldg(posC + r) : -2);
+                    ak[k] = bt == 0 ? ak0[k] : ((LIVE && r < r_hi) ? __ldg(rowp + r) : (real)0);
+                    if (!LIVE || r == 0 || r == rq || r >= r_hi) pos[k] = -2;
+                }
+                // -2: final in the tableau (rows 0 and 1+q' were finished by stages 0 / R; quiescent tableau)
+                // -1: apply the running update here: not in the running list (a_pr == 0, no tile touches it), or held old by
+                //     its claimer
+                // >= 0 after classification: updated in full by its tile, read the new value once that tile is complete
+                // All records are fetched at once; only tiles still in flight are polled.
+#pragma unroll
+                for (int k = 0; k < kLaRB; ++k) {
+                    rec[k] = 0u;
+                    if (pos[k] >= 0) {
+                        const long long tmap = (pos[k] / tile_rows) * P.nchunks + chunk;
+                        const long long t = reverse ? (ntiles - 1 - tmap) : tmap;
+                        if (t >= c_col + base)
+                            pos[k] = -1;
+                        else
+                            rec[k] = ld_relaxed_u32(P.tile_rec + tmap);
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < kLaRB; ++k) {
+                    if (pos[k] >= 0) {
+                        if ((rec[k] & ~kRecHeld) != seq) {
+                            const long long tmap = (pos[k] / tile_rows) * P.nchunks + chunk;
+                            rec[k] = la_poll_rec(P.tile_rec + tmap, seq, cyc);
+                            if ((rec[k] & ~kRecHeld) != seq) bad = 1;
+                        }
+                        pos[k] = (rec[k] & kRecHeld) ? -1 : -2;
+                    }
+                }
+                __threadfence();   // (acquire side of the relaxed record loads)
+#pragma unroll
+                for (int k = 0; k < kLaRB; ++k) {
+                    const long long r = rb0 + (long long)k * kSelBlock;
+                    v[k] = (r < r_hi) ? __ldcg(P.T + r * P.ld + lpn) : (real)0;
+                }
+#pragma unroll
+                for (int k = 0; k < kLaRB; ++k)
+                    if (pos[k] == -1) v[k] = fma_r(sp, ak[k], v[k]);
+            }
+            if (owner) {
+#pragma unroll
+                for (int k = 0; k < kLaRB; ++k) {
+                    const long long r = rb0 + (long long)k * kSelBlock;
+                    if (r < r_hi) {
+                        if (!sharded) {
+                            rowpN[r] = v[k];
+                        } else {
+#pragma unroll 1
+                            for (int wr = 0; wr < P.world; ++wr) arena_rowp(P, wr, tpar)[r] = v[k];
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < kLaRB; ++k) {
+                const long long r = rb0 + (long long)k * kSelBlock;
+                const int live = (r < r_hi && r != 0 && (!skip || v[k] != (real)0)) ? 1 : 0;
+                mine_cnt += __syncthreads_count(live);
+            }
+            if (bt == 0) {
+#pragma unroll
+                for (int k = 0; k < kLaRB; ++k) v0[k] = v[k];
+            }
+        }
+        bad = __syncthreads_or(bad);
+        if (sharded && owner) {
+            // my slice is in every arena: tell helper h of every rank
+            // (release is cumulative over the stores the barrier above ordered before it)
+            if (threadIdx.x < P.world) st_release_sys(&arena_of(P, threadIdx.x)->la_flag_rowp[tpar][h], (unsigned long long)tseq);
+        }
+        if (threadIdx.x == 0) {
+            if (bad) nxt->status_next = kStatusPeerTimeout;
+            la->cnt[h] = mine_cnt;
+            st_release_u32(&la->cnt_seq[h], tseq);
+        }
+    }
+    // ---- stage S: everybody's counts -> list offsets; s' = -col'/pivot' for the local slab; the row list -------------
+    if (!la_wait_many_u32(la->cnt_seq, H, tseq, cyc)) {
+        if (threadIdx.x == 0) nxt->status_next = kStatusPeerTimeout;
+        return;
     }
     if (h == 0 && threadIdx.x == 0) la->stamps[4] = globaltimer();
+    // (LIVE) every helper has classified its rows: the streaming CTAs may stop writing tile records
+    if (LIVE && h == 0 && threadIdx.x == 0) atomicOr(&la->word, kQuietBit);
+    int cnts = 0;
+    if ((int)threadIdx.x < H) cnts = __ldcg(&la->cnt[threadIdx.x]);
     const real pivn = __ldcg(rowpN + rq);   // a_pq = T[1+q'][p']
-    for (long long i = (long long)h * kSelBlock + threadIdx.x; i < P.ld; i += (long long)H * kSelBlock)
-        sN[i] = (i < P.m_loc && i != lpn) ? div_r(-__ldcg(colN + i), pivn) : (real)0;
+    real cv[kLaBB];
+#pragma unroll
+    for (int k = 0; k < kLaBB; ++k) {
+        const long long i = (long long)h * kSelBlock + threadIdx.x + (long long)k * H * kSelBlock;
+        cv[k] = (i < P.m_loc) ? __ldcg(colN + i) : (real)0;
+    }
+    int offset = 0, total = 0;
+    if (threadIdx.x < 32) {   // H <= 16 counts live in the first lanes of warp 0
+#pragma unroll
+        for (int k = 0; k < kLaMaxHelpers; ++k) {
+            const int ck = __shfl_sync(0xffffffffu, cnts, k);
+            if (k < H) {
+                if (k < h) offset += ck;
+                total += ck;
+            }
+        }
+        if (threadIdx.x == 0) {
+            sh.i0 = offset;
+            sh.i1 = total;
+        }
+    }
+    __syncthreads();
+    offset = sh.i0;
+    total = sh.i1;
+    __syncthreads();
+    for (long long i0 = (long long)h * kSelBlock + threadIdx.x; i0 < P.ld; i0 += (long long)H * kSelBlock * kLaBB) {
+        const bool first = i0 == (long long)h * kSelBlock + threadIdx.x;
+#pragma unroll
+        for (int k = 0; k < kLaBB; ++k) {
+            const long long i = i0 + (long long)k * H * kSelBlock;
+            if (i < P.ld) {
+                const real cvk = first ? cv[k] : ((i < P.m_loc) ? __ldcg(colN + i) : (real)0);
+                sN[i] = (i < P.m_loc && i != lpn) ? la_div(-cvk, pivn) : (real)0;
+            }
+        }
+    }
     {
-        // Row list: helper h compacts the contiguous slice [r_lo, r_hi) of stored rows.  Pass 1 counts, the counts are
-        // exchanged through LaState, pass 2 writes (row, a_pr) pairs in ascending row order.
         int* listN = P.rowlist + (size_t)tpar * P.rowp_stride;
         real* valN = P.rowval + (size_t)tpar * P.rowp_stride;
         int* posN = P.rowpos + (size_t)tpar * P.rowp_stride;
-        const long long slice = (((P.Rs + H - 1) / H) + kSelBlock - 1) / kSelBlock * kSelBlock;
-        const long long r_lo = (long long)h * slice, r_hi = (r_lo + slice < P.Rs) ? r_lo + slice : P.Rs;
-        const bool skip = P.skip_zero != 0;
-        int mine = 0;
-        for (long long c0 = r_lo; c0 < r_hi; c0 += kSelBlock) {
-            const long long r = c0 + threadIdx.x;
-            const int live = (r < r_hi && r != 0 && (!skip || __ldcg(rowpN + r) != (real)0)) ? 1 : 0;
-            mine += __syncthreads_count(live);
-        }
-        if (threadIdx.x == 0) {
-            la->cnt[h] = mine;
-            __threadfence();
-            st_release_u32(&la->cnt_seq[h], tseq);
-        }
-        int okk = 1;
-        if (threadIdx.x < H) {
-            const long long t0 = clock64();
-            while (ld_acquire_u32(&la->cnt_seq[threadIdx.x]) != tseq) {
-                if (clock64() - t0 > cyc) {
-                    okk = 0;
-                    break;
-                }
-            }
-        }
-        if (!__syncthreads_and(okk)) {
-            if (threadIdx.x == 0) nxt->status_next = kStatusPeerTimeout;
-            return;
-        }
-        __threadfence();
-        int offset = 0, total = 0;
-        for (int k = 0; k < H; ++k) {
-            const int ck = __ldcg(&la->cnt[k]);
-            if (k < h) offset += ck;
-            total += ck;
-        }
-        int* s_w = reinterpret_cast<int*>(&sm);   // 16 warp totals (the tree buffers are idle here)
         const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-        for (long long c0 = r_lo; c0 < r_hi; c0 += kSelBlock) {
-            const long long r = c0 + threadIdx.x;
-            real v = (real)0;
-            if (r < r_hi) v = __ldcg(rowpN + r);
-            const int live = (r < r_hi && r != 0 && (!skip || v != (real)0)) ? 1 : 0;
-            const unsigned bal = __ballot_sync(0xffffffffu, live);
-            if (lane == 0) s_w[wid] = __popc(bal);
-            __syncthreads();
-            int before = 0, chunk_total = 0;
+        for (int bt = 0; bt < nbatch; ++bt) {
+            real v[kLaRB];
+            const long long rb0 = r_lo + (long long)bt * kLaRB * kSelBlock + threadIdx.x;
+            if (bt == 0) {
 #pragma unroll
-            for (int k = 0; k < kSelBlock / 32; ++k) {
-                const int wk = s_w[k];
-                if (k < wid) before += wk;
-                chunk_total += wk;
-            }
-            const int pos = offset + before + __popc(bal & ((1u << lane) - 1u));
-            if (r < r_hi) {
-                if (live) {
-                    listN[pos] = (int)r;
-                    valN[pos] = v;
-                    posN[r] = pos;
-                } else {
-                    posN[r] = -1;
+                for (int k = 0; k < kLaRB; ++k) v[k] = v0[k];
+            } else {
+#pragma unroll
+                for (int k = 0; k < kLaRB; ++k) {
+                    const long long r = rb0 + (long long)k * kSelBlock;
+                    v[k] = (r < r_hi) ? __ldcg(rowpN + r) : (real)0;
                 }
             }
-            offset += chunk_total;
+            unsigned bal[kLaRB];
+#pragma unroll
+            for (int k = 0; k < kLaRB; ++k) {
+                const long long r = rb0 + (long long)k * kSelBlock;
+                const int live = (r < r_hi && r != 0 && (!skip || v[k] != (real)0)) ? 1 : 0;
+                bal[k] = __ballot_sync(0xffffffffu, live);
+                if (lane == 0) s_scan[k][wid] = __popc(bal[k]);
+            }
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < kLaRB; ++k) {
+                const long long r = rb0 + (long long)k * kSelBlock;
+                int before = 0, chunk_total = 0;
+#pragma unroll
+                for (int wq = 0; wq < kSelBlock / 32; ++wq) {
+                    const int c = s_scan[k][wq];
+                    if (wq < wid) before += c;
+                    chunk_total += c;
+                }
+                if (r < r_hi) {
+                    if ((bal[k] >> lane) & 1u) {
+                        const int pos = offset + before + __popc(bal[k] & ((1u << lane) - 1u));
+                        listN[pos] = (int)r;
+                        valN[pos] = v[k];
+                        posN[r] = pos;
+                    } else {
+                        posN[r] = -1;
+                    }
+                }
+                offset += chunk_total;
+            }
             __syncthreads();
         }
         if (h == 0 && threadIdx.x == 0) {
             nxt->nz = total;
             nxt->piv = (double)pivn;
-            nxt->sc = (double)div_r(-cqn, pivn);   // src/solver.cu:54
+            nxt->sc = (double)la_div(-cqn, pivn);   // src/solver.cu:54
         }
     }
+    // done: the proposal is complete once every helper has said so (checked by the CTA that commits the pivot)
+    __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence();
-        const unsigned t = atomicAdd(&la->ticket_s, 1u);
-        if (t == (unsigned)H - 1u) {
-            la->ticket_s = 0;
-            __threadfence();
-            st_release_u32(&nxt->ready_seq, tseq);
-            la->stamps[5] = globaltimer();
-        }
+        st_release_u32(&la->done_seq[h], tseq);
+        if (h == 0) la->stamps[5] = globaltimer();
     }
+}
+
+// After the chain: the verdict for pivot tseq.  kRunning (and the proposal is marked ready) iff every helper finished;
+// the phase-ending status the chain found (kFeasible / kUnbounded); kStatusPeerTimeout when somebody stopped publishing.
+__device__ __forceinline__ int la_finalize(LaState* la, Proposal* nxt, unsigned tseq, int H, bool live)
+{
+    if (live && __ldcg(&nxt->q_seq) != tseq) return kStatusPeerTimeout;
+    const int sn = __ldcg(&nxt->status_next);
+    if (sn != kRunning) return sn;
+    for (int k = 0; k < H; ++k)
+        if (__ldcg(&la->done_seq[k]) != tseq) return kStatusPeerTimeout;
+    nxt->ready_seq = tseq;
+    return kRunning;
 }
 
 // ---------------------------------------------------------------------------------------------
 // update_la_kernel -- see the header of this file.  256-bit accesses, 8 rows in flight per thread, tiles of
 // (512 >> log2_tpr) * 8 list rows x one column chunk, handed out by the ticket word.
 // ---------------------------------------------------------------------------------------------
-template <typename real>
+template <typename real, int U>
 __global__ void __launch_bounds__(kSelBlock, 1) update_la_kernel(const __grid_constant__ PivotParams<real> P)
 {
-    constexpr int VB = 32, U = 8;
+    constexpr int VB = 32;
     constexpr int EPT = VB / (int)sizeof(real);
     __shared__ TreeSmem<real> sm;
     __shared__ real smax[32];
@@ -686,8 +914,14 @@ __global__ void __launch_bounds__(kSelBlock, 1) update_la_kernel(const __grid_co
     const int ntiles = ((nlive + tile_rows - 1) / tile_rows) * P.nchunks;
     if (blockIdx.x == 0 && threadIdx.x == 0) la->stamps[0] = globaltimer();
 
-    if ((int)blockIdx.x < P.Gc)
-        la_cost_blocks<real>(P, la, &la->prop[par ^ 1], seq + 1u, rowp, (real)__ldcg(&cur->sc), sm, sh);
+    {
+        // cost update + entering tournament on the first non-helper CTAs, so that the helpers start on the RHS row at once
+        const int first = ((int)gridDim.x > H) ? H : 0;
+        const int ncta = (int)gridDim.x - first;
+        if ((int)blockIdx.x >= first && (int)blockIdx.x - first < P.Gc)
+            la_cost_blocks<real>(P, la, &la->prop[par ^ 1], seq + 1u, rowp, (real)__ldcg(&cur->sc), first, ncta,
+                                 P.rowpos + (size_t)par * P.rowp_stride, tile_rows, sm, sh);
+    }
     if (helper)
         la_chain<real, true>(P, la, seq, (int)blockIdx.x, H, rowp, svec, (real)__ldcg(&cur->piv), (long long)lp, p, q, reverse,
                              (long long)ntiles, sm, smax, sh);
@@ -709,12 +943,16 @@ __global__ void __launch_bounds__(kSelBlock, 1) update_la_kernel(const __grid_co
             ts.word[0] = helper ? atomicAdd(&la->word, 1ull) : 0ull;
         }
         __syncthreads();
-        int tile, skip_row, skip_col;
-        {
-            const unsigned long long w = ts.word[0];
-            tile = helper ? (int)(w & kTicketMask) + base : (int)blockIdx.x - H;
-            skip_row = helper ? (int)((w >> kTicketBits) & kRowMask) - 1 : -1;
-            skip_col = helper ? (int)(w >> kColShift) - 1 : -1;
+        int tile, skip_row = -1, skip_col = -1;
+        bool want_rec = true;
+        if (helper) {
+            const LaClaim cl = la_decode(ts.word[0]);
+            tile = cl.tile + base;
+            skip_row = cl.skip_row;
+            skip_col = cl.skip_col;
+            want_rec = cl.record;
+        } else {
+            tile = (int)blockIdx.x - H;
         }
         if (tile < ntiles) {
             const int tmap0 = reverse ? (ntiles - 1 - tile) : tile;
@@ -727,6 +965,7 @@ __global__ void __launch_bounds__(kSelBlock, 1) update_la_kernel(const __grid_co
         }
         __syncthreads();
         int rec_pending = -1;   // thread 0: tile whose completion record is still to be written
+        unsigned rec_value = seq;
         int cur_chunk = -1;
         real sreg[EPT];
         while (tile < ntiles) {
@@ -754,7 +993,7 @@ __global__ void __launch_bounds__(kSelBlock, 1) update_la_kernel(const __grid_co
             }
             if (threadIdx.x < 32) {
                 // warp 0: the record of the previous tile goes out, the next tile's list entries come in
-                if (threadIdx.x == 0 && rec_pending >= 0) st_release_u32(P.tile_rec + rec_pending, seq);
+                if (threadIdx.x == 0 && rec_pending >= 0) st_release_u32(P.tile_rec + rec_pending, rec_value);
                 wnext = __shfl_sync(0xffffffffu, wnext, 0);
                 const int ntile = (int)(wnext & kTicketMask) + base;
                 if (threadIdx.x == 0) ts.word[buf ^ 1] = wnext;
@@ -788,16 +1027,18 @@ __global__ void __launch_bounds__(kSelBlock, 1) update_la_kernel(const __grid_co
                     if (r >= 0 && r != skip_row) P.T[(long long)r * P.ld + lp] = div_r(ts.val[buf][ty + u * rpp], pv);
                 }
             }
-            // tiles claimed after both publications are never waited for: no record needed
-            rec_pending = (skip_col >= 0) ? -1 : tmap;
+            // the record says whether this tile held the published column old; once the helpers are done nobody reads records
+            rec_pending = want_rec ? tmap : -1;
+            rec_value = seq | (skip_col >= 0 ? kRecHeld : 0u);
             __syncthreads();
             buf ^= 1;
-            const unsigned long long w = ts.word[buf];
-            tile = (int)(w & kTicketMask) + base;
-            skip_row = (int)((w >> kTicketBits) & kRowMask) - 1;
-            skip_col = (int)(w >> kColShift) - 1;
+            const LaClaim cl = la_decode(ts.word[buf]);
+            tile = cl.tile + base;
+            skip_row = cl.skip_row;
+            skip_col = cl.skip_col;
+            want_rec = cl.record;
         }
-        if (threadIdx.x == 0 && rec_pending >= 0) st_release_u32(P.tile_rec + rec_pending, seq);
+        if (threadIdx.x == 0 && rec_pending >= 0) st_release_u32(P.tile_rec + rec_pending, rec_value);
     }
 
     // ---- the last CTA to leave commits the pivot and re-arms the ticket word -------------------------------
@@ -806,7 +1047,7 @@ __global__ void __launch_bounds__(kSelBlock, 1) update_la_kernel(const __grid_co
         const unsigned done = atomicAdd(&la->tile_done, 1u);
         if (done == gridDim.x - 1) {
             __threadfence();
-            const Proposal* nxt = &la->prop[par ^ 1];
+            Proposal* nxt = &la->prop[par ^ 1];
             P.base[p] = q;   // src/solver.cu:105
             if (pivots < P.trace_cap) P.trace[pivots] = make_int2(q, p);
             unsigned long long hsh = st->hash;
@@ -822,14 +1063,7 @@ __global__ void __launch_bounds__(kSelBlock, 1) update_la_kernel(const __grid_co
             st->q = q;
             st->p = p;
             st->rows_streamed += (long long)nlive + 1;
-            int next_status = kStatusPeerTimeout;   // an incomplete chain means somebody stopped publishing
-            if (__ldcg(&nxt->q_seq) == seq + 1u) {
-                const int sn = __ldcg(&nxt->status_next);
-                if (sn != kRunning)
-                    next_status = sn;
-                else if (__ldcg(&nxt->ready_seq) == seq + 1u)
-                    next_status = kRunning;
-            }
+            const int next_status = la_finalize(la, nxt, seq + 1u, H, true);
             st->status = next_status;
             st->pivots = pivots + 1;
             la->word = 0ull;
@@ -867,10 +1101,10 @@ __global__ void la_prologue_commit_kernel(PivotParams<real> P)
     DevState* st = P.st;
     if (__ldcg(&st->status) != kRunning || __ldcg(&st->pivots) >= __ldcg(&st->limit)) return;
     const unsigned tseq = (unsigned)(__ldcg(&st->pivots) + 1);
-    const Proposal* nxt = &P.la->prop[tseq & 1u];
+    Proposal* nxt = &P.la->prop[tseq & 1u];
     if (__ldcg(&nxt->ready_seq) == tseq) return;
-    const int sn = __ldcg(&nxt->status_next);
-    st->status = (__ldcg(&nxt->p_seq) == tseq && sn != kRunning) ? sn : kStatusPeerTimeout;
+    const int sn = la_finalize(P.la, nxt, tseq, P.helpers, false);
+    if (sn != kRunning) st->status = sn;
 }
 
 // Write the prepared pivot constraint back into its (possibly held-old) tableau column, so that the host --

@@ -152,7 +152,8 @@ struct SolverImpl final : SolverBase {
     real *col2 = nullptr, *s2 = nullptr, *rowp2 = nullptr, *rowval = nullptr;
     int *rowlist = nullptr, *rowpos = nullptr;
     int la_grid = 0;
-    int la_helpers = 0;   // 0 = choose: 4 on one GPU, 8 when sharded (the chain then contains two NVLink round trips)
+    int la_u = 8;
+    int la_helpers = 0;   // 0 = default: 8 on one GPU (chain hidden anyway), 16 when sharded (the chain is the critical path)
     long long wait_cycles = 4000000000ll;
     int fault_rank = -1;
     long long fault_pivot = 0;
@@ -270,6 +271,7 @@ struct SolverImpl final : SolverBase {
         CK(cudaMemsetAsync(st, 0, sizeof(DevState), stream));  // `stream` is non-blocking: never mix in legacy-stream calls
         CK(cudaMalloc(&la, sizeof(LaState)));
         CK(cudaMemsetAsync(la, 0, sizeof(LaState), stream));
+        if (const char* e = getenv("B2S_LA_U")) la_u = atoi(e) == 4 ? 4 : 8;
         if (const char* e = getenv("B2S_LA_HELPERS")) la_helpers = std::max(1, std::min(kLaMaxHelpers, atoi(e)));
         if (const char* e = getenv("B2S_PEER_TIMEOUT_MS")) wait_cycles = std::max(1ll, atoll(e)) * 2000000ll;  // ~2 GHz
         if (const char* e = getenv("B2S_FAULT_RANK")) fault_rank = atoi(e);
@@ -471,6 +473,8 @@ struct SolverImpl final : SolverBase {
         if (R1 >= (long long)kRowMask - 1 || ld >= (long long)kNoColumn - 1) return false;  // ticket-word fields
         return true;
     }
+    typedef void (*LaFn)(const PivotParams<real>);
+    LaFn la_fn() const { return la_u == 4 ? (LaFn)update_la_kernel<real, 4> : (LaFn)update_la_kernel<real, 8>; }
     typedef void (*LoopFn)(PivotParams<real>, int);
     LoopFn loop_fn() const
     {
@@ -579,8 +583,9 @@ struct SolverImpl final : SolverBase {
         }
         // look-ahead kernel: same tile geometry as variant 8; tiles are cut from the per-pivot row list, so size by the maximum
         {
-            const long long rows_tile8 = (long long)rpp * 8;
+            const long long rows_tile8 = (long long)rpp * la_u;
             const long long max_tiles = ((R1 + rows_tile8 - 1) / rows_tile8 + 1) * P.nchunks;
+            P.la_u = la_u;
             if ((size_t)max_tiles > cap_tiles) {
                 cudaFree(tile_rec);
                 tile_rec = nullptr;
@@ -590,7 +595,7 @@ struct SolverImpl final : SolverBase {
                     cudaMemsetAsync(tile_rec, 0, sizeof(unsigned) * cap_tiles, stream);
                 }
             }
-            const int want = la_helpers > 0 ? la_helpers : (world > 1 ? 8 : 4);   // measured: profiles/r02_lookahead.md
+            const int want = la_helpers > 0 ? la_helpers : (world > 1 ? 16 : 8);   // measured: profiles/r02_lookahead.md   // measured: profiles/r02_lookahead.md
             la_grid = (int)std::max<long long>(1, std::min<long long>(num_sms, std::max<long long>(max_tiles + want, P.Gc)));
             P.helpers = std::min(want, la_grid);
             P.la = la;
@@ -808,7 +813,7 @@ struct SolverImpl final : SolverBase {
     {
         if (use_lookahead()) {
             // one launch per pivot: streaming update + the next pivot's selection (and, sharded, its two exchanges) under it
-            update_la_kernel<real><<<la_grid, kSelBlock, 0, stream>>>(P);
+            la_fn()<<<la_grid, kSelBlock, 0, stream>>>(P);
             return B2S_OK;
         }
         if (world > 1 && p2p) {
@@ -1528,7 +1533,7 @@ struct SolverImpl final : SolverBase {
         long long made = 0;
         for (int k = 0; k < count; ++k) {
             CK(cudaEventRecord(ev[2 * k], stream));
-            update_la_kernel<real><<<la_grid, kSelBlock, 0, stream>>>(P);
+            la_fn()<<<la_grid, kSelBlock, 0, stream>>>(P);
             CK(cudaEventRecord(ev[2 * k + 1], stream));
             if (stage_us) {   // the stamps are per pivot: read them before the next launch overwrites them
                 CK(cudaMemcpyAsync(&snap[(size_t)k], la, sizeof(LaState), cudaMemcpyDeviceToHost, stream));
