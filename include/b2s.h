@@ -203,6 +203,15 @@ int b2s_dist_unique_id(char id[B2S_NCCL_ID_BYTES]); /* rank 0 creates, the host 
  * owns constraints [r*m/world, (r+1)*m/world) of every tableau row; m/world must be a multiple of 512. */
 int b2s_dist_init(b2s_solver *s, int rank, int world, const char id[B2S_NCCL_ID_BYTES]);
 
+/* The same without NCCL: the ranks are bootstrapped through the caller's own all-gather (MPI, torch.distributed/gloo, sockets
+ * ...).  `allgather(user, send, recv, bytes)` must deliver every rank's `bytes` bytes, in rank order, into recv (world * bytes,
+ * host memory) on every rank and return 0; the library calls it, collectively and in the same order on all ranks, for the
+ * CUDA-IPC handles of the peer-memory arenas, for barriers, for the price-out chain and for the solution vector.  The per-pivot
+ * exchanges are peer-memory kernels (NVLink between GPUs; plain device memory when several ranks share one GPU, which is how
+ * the driver's single-GPU test tier runs the sharded kernels).  At most 8 ranks. */
+typedef int (*b2s_allgather_fn)(void *user, const void *send, void *recv, size_t bytes);
+int b2s_dist_init_host(b2s_solver *s, int rank, int world, b2s_allgather_fn allgather, void *user);
+
 #ifdef __cplusplus
 }
 #endif

@@ -77,9 +77,12 @@ SIGNATURES = {
     "b2s_profile_pivots": (C.c_int, [_P, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), _LL]),
     "b2s_get_loop_info": (C.c_int, [_P, _I, _I, _I]),
     "b2s_profile_lookahead": (C.c_int, [_P, C.c_int, C.POINTER(C.c_float), _D, _LL]),
+    "b2s_dist_init_host": (C.c_int, [_P, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "b2s_dist_unique_id": (C.c_int, [C.c_char_p]),
     "b2s_dist_init": (C.c_int, [_P, C.c_int, C.c_int, C.c_char_p]),
 }
+
+ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t)  # b2s_allgather_fn
 
 _lib = None
 

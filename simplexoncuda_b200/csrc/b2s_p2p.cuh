@@ -37,11 +37,11 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 }
 // Poll a flag in local memory until it reaches seq.  Bounded: ~2 s at the B200's clock, then give up
 // (the caller turns that into kStatusPeerTimeout) so a dead peer cannot hang the GPU.
-__device__ __forceinline__ bool wait_flag(const unsigned long long* flag, unsigned long long seq)
+__device__ __forceinline__ bool wait_flag(const unsigned long long* flag, unsigned long long seq, long long cycles = 4000000000ll)
 {
     const long long t0 = clock64();
     while (ld_acquire_sys(flag) < seq) {
-        if (clock64() - t0 > 4000000000ll) return false;
+        if (clock64() - t0 > cycles) return false;
         __nanosleep(64);
     }
     return true;
@@ -117,9 +117,10 @@ __global__ void __launch_bounds__(kSelBlock) ratio_p2p_kernel(PivotParams<real> 
     if (!s_flag) return;
     // last CTA of this rank: all local winners are out -> raise our flag everywhere, wait for everyone's
     __threadfence_system();
-    if (threadIdx.x < P.world) st_release_sys(&arena_of(P, threadIdx.x)->flag_slots[par][P.rank], seq);
+    const bool mute = P.fault_rank == P.rank && (long long)seq >= P.fault_pivot;   // fault injection (tests): this rank goes silent
+    if (threadIdx.x < P.world && !mute) st_release_sys(&arena_of(P, threadIdx.x)->flag_slots[par][P.rank], seq);
     int ok = 1;
-    if (threadIdx.x < P.world) ok = wait_flag(&arena_of(P, P.rank)->flag_slots[par][threadIdx.x], seq) ? 1 : 0;
+    if (threadIdx.x < P.world) ok = wait_flag(&arena_of(P, P.rank)->flag_slots[par][threadIdx.x], seq, P.wait_cycles) ? 1 : 0;
     ok = __syncthreads_and(ok);
     if (!ok) {
         if (threadIdx.x == 0) {
@@ -176,7 +177,7 @@ __global__ void __launch_bounds__(256) svec_p2p_kernel(PivotParams<real> P)
     if (!__ldcg(&st->live)) return;
     const unsigned long long seq = (unsigned long long)__ldcg(&st->pivots);
     const int par = (int)(seq & 1ull);
-    if (threadIdx.x == 0) s_ok = wait_flag(&arena_of(P, P.rank)->flag_rowp[par], seq) ? 1 : 0;
+    if (threadIdx.x == 0) s_ok = wait_flag(&arena_of(P, P.rank)->flag_rowp[par], seq, P.wait_cycles) ? 1 : 0;
     __syncthreads();
     if (!s_ok) {
         if (threadIdx.x == 0) st->status = kStatusPeerTimeout;  // update_kernel still sees live: make it stop too

@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(kSelBlock, 1) pivot_loop_kernel(const __grid_c
                 st_release_sys(&arena_of(P, threadIdx.x)->flag_slots[par][P.rank], seq);
             }
             int ok = 1;
-            if (threadIdx.x < P.world) ok = wait_flag(&arena_of(P, P.rank)->flag_slots[par][threadIdx.x], seq) ? 1 : 0;
+            if (threadIdx.x < P.world) ok = wait_flag(&arena_of(P, P.rank)->flag_slots[par][threadIdx.x], seq, P.wait_cycles) ? 1 : 0;
             ok = __syncthreads_and(ok);
             if (!ok) {
                 if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(kSelBlock, 1) pivot_loop_kernel(const __grid_c
                 __threadfence_system();
                 st_release_sys(&arena_of(P, threadIdx.x)->flag_rowp[par], seq);
             }
-            if (threadIdx.x == 0) s_ok = wait_flag(&arena_of(P, P.rank)->flag_rowp[par], seq) ? 1 : 0;
+            if (threadIdx.x == 0) s_ok = wait_flag(&arena_of(P, P.rank)->flag_rowp[par], seq, P.wait_cycles) ? 1 : 0;
             __syncthreads();
             if (!s_ok) {
                 if (blockIdx.x == 0 && threadIdx.x == 0) {

@@ -61,6 +61,7 @@ struct SolverBase {
     virtual int max_le_zero_device(const double* dvec, long long n, int* result) = 0;
     virtual int bench_update(int launches, int flush, float* ms, double* bytes) = 0;
     virtual int dist_init(int rank, int world, const char* id) = 0;
+    virtual int dist_init_host(int rank, int world, b2s_allgather_fn fn, void* user) = 0;
     virtual int profile_pivots(int count, float* ms_ratio, float* ms_gather, float* ms_update, long long* done) = 0;
     virtual int profile_lookahead(int count, float* kernel_ms, double* stage_us, long long* done) = 0;
     virtual int loop_info(int* launches, int* lookahead, int* persistent) = 0;
@@ -172,6 +173,10 @@ struct SolverImpl final : SolverBase {
 #ifdef B2S_WITH_NCCL
     ncclComm_t comm = nullptr;
 #endif
+    // Host-layer collectives instead of NCCL (b2s_dist_init_host): the caller's all-gather moves the few bytes the slow paths
+    // need (IPC handles, barriers, the price-out chain, the solution); the per-pivot exchanges are peer-memory kernels anyway.
+    b2s_allgather_fn host_ag = nullptr;
+    void* host_ag_user = nullptr;
     // peer-memory exchange (b2s_p2p.cuh)
     bool use_pdl = false;          // single-GPU launches path: programmatic dependent launch between the 3 kernels
     bool p2p = false;              // arenas mapped on every rank: the per-pivot exchanges bypass NCCL
@@ -306,14 +311,45 @@ struct SolverImpl final : SolverBase {
         p2p = false;
     }
 
+    bool have_collectives() const
+    {
+#ifdef B2S_WITH_NCCL
+        if (comm) return true;
+#endif
+        return host_ag != nullptr;
+    }
+    // every rank contributes `bytes` bytes; recv holds world * bytes (host memory)
+    int host_allgather(const void* send, void* recv, size_t bytes)
+    {
+        if (!host_ag) return fail(B2S_ERR_STATE, "no host all-gather registered");
+        if (host_ag(host_ag_user, send, recv, bytes) != 0) return fail(B2S_ERR_NCCL, "host all-gather callback failed");
+        return B2S_OK;
+    }
+    // all ranks have executed everything enqueued so far
+    int rank_barrier()
+    {
+        if (world <= 1) return B2S_OK;
+#ifdef B2S_WITH_NCCL
+        if (comm) {
+            NK(ncclAllReduce(verdict, verdict, 1, ncclInt, ncclSum, comm, stream));
+            return B2S_OK;
+        }
+#endif
+        CK(cudaStreamSynchronize(stream));
+        std::vector<int> box((size_t)world);
+        const int mine = rank;
+        return host_allgather(&mine, box.data(), sizeof(int));
+    }
+
     // Sharded solves: (re)create this rank's arena for `rows` pivot-constraint entries and map every
     // peer's arena (CUDA IPC handles travel through one ncclAllGather).  Collective over the ranks.
     int ensure_arena(long long rows)
     {
-#ifdef B2S_WITH_NCCL
         if (world <= 1) return B2S_OK;
         const char* env = getenv("B2S_P2P");
         if ((env && atoi(env) == 0) || world > kMaxPeers) {
+            if (host_ag) return fail(B2S_ERR_STATE, "a solver bootstrapped through the host layer needs the peer-memory exchanges (B2S_P2P=0 "
+                                                    "and more than %d ranks are NCCL-only)", kMaxPeers);
             close_arena();
             return B2S_OK;
         }
@@ -324,15 +360,26 @@ struct SolverImpl final : SolverBase {
         CK(cudaMemsetAsync(arena, 0, arena_bytes<real>(cap), stream));
         cudaIpcMemHandle_t mine;
         CK(cudaIpcGetMemHandle(&mine, arena));
-        unsigned char* hbuf = nullptr;
-        CK(cudaMalloc(&hbuf, sizeof(mine) * (size_t)world));
-        CK(cudaMemcpyAsync(hbuf + sizeof(mine) * (size_t)rank, &mine, sizeof(mine), cudaMemcpyHostToDevice, stream));
-        NK(ncclAllGather(hbuf + sizeof(mine) * (size_t)rank, hbuf, sizeof(mine), ncclChar, comm, stream));
-        CK(cudaStreamSynchronize(stream));
         std::vector<cudaIpcMemHandle_t> all((size_t)world);
-        CK(cudaMemcpyAsync(all.data(), hbuf, sizeof(mine) * (size_t)world, cudaMemcpyDeviceToHost, stream));
-        CK(cudaStreamSynchronize(stream));
-        cudaFree(hbuf);
+        bool gathered = false;
+#ifdef B2S_WITH_NCCL
+        if (comm) {
+            unsigned char* hbuf = nullptr;
+            CK(cudaMalloc(&hbuf, sizeof(mine) * (size_t)world));
+            CK(cudaMemcpyAsync(hbuf + sizeof(mine) * (size_t)rank, &mine, sizeof(mine), cudaMemcpyHostToDevice, stream));
+            NK(ncclAllGather(hbuf + sizeof(mine) * (size_t)rank, hbuf, sizeof(mine), ncclChar, comm, stream));
+            CK(cudaStreamSynchronize(stream));
+            CK(cudaMemcpyAsync(all.data(), hbuf, sizeof(mine) * (size_t)world, cudaMemcpyDeviceToHost, stream));
+            CK(cudaStreamSynchronize(stream));
+            cudaFree(hbuf);
+            gathered = true;
+        }
+#endif
+        if (!gathered) {
+            CK(cudaStreamSynchronize(stream));   // the arena is zeroed before anybody can map and write it
+            int rc = host_allgather(&mine, all.data(), sizeof(mine));
+            if (rc) return rc;
+        }
         for (int r = 0; r < world; ++r) {
             if (r == rank) {
                 peer_ptr[r] = arena;
@@ -344,9 +391,6 @@ struct SolverImpl final : SolverBase {
         }
         arena_rows = cap;
         p2p = true;
-#else
-        (void)rows;
-#endif
         return B2S_OK;
     }
 
@@ -755,14 +799,13 @@ struct SolverImpl final : SolverBase {
             int rc = reset_lookahead();
             if (rc) return rc;
         }
-#ifdef B2S_WITH_NCCL
         if (p2p) {
             // pivot sequence numbers restart at 1: clear this rank's flags, then make sure every rank
-            // has done so before anyone can publish (the all-reduce is the barrier).
+            // has done so before anyone can publish
             CK(cudaMemsetAsync(arena, 0, sizeof(ArenaHeader<real>), stream));
-            NK(ncclAllReduce(verdict, verdict, 1, ncclInt, ncclSum, comm, stream));
+            int rc = rank_barrier();
+            if (rc) return rc;
         }
-#endif
         stage = kBuilt;
         return B2S_OK;
     }
@@ -774,17 +817,30 @@ struct SolverImpl final : SolverBase {
         coef_kernel<real><<<(unsigned)((m_loc + 255) / 256), 256, 0, stream>>>(P, coef);
         const long long threads = Rc * 32;
         const unsigned blocks = (unsigned)((threads + 255) / 256);
-#ifdef B2S_WITH_NCCL
         if (world > 1) {
             // Chain the running sums through the ranks in ascending constraint order so the result is
             // bit-identical to the single-GPU order (slabs are multiples of 64 constraints).
+            std::vector<real> hbuf;
             for (int r = 0; r < world; ++r) {
                 if (r == rank) priceout_kernel<real><<<blocks, 256, 0, stream>>>(P, coef);
-                NK(ncclBroadcast(cost, cost, (size_t)Rc * sizeof(real), ncclChar, r, comm, stream));
-            }
-        } else
+                bool sent = false;
+#ifdef B2S_WITH_NCCL
+                if (comm) {
+                    NK(ncclBroadcast(cost, cost, (size_t)Rc * sizeof(real), ncclChar, r, comm, stream));
+                    sent = true;
+                }
 #endif
-        {
+                if (!sent) {   // host layer: everybody contributes its vector, rank r's is the one that counts
+                    hbuf.resize((size_t)Rc * (size_t)(world + 1));
+                    CK(cudaMemcpyAsync(hbuf.data(), cost, sizeof(real) * (size_t)Rc, cudaMemcpyDeviceToHost, stream));
+                    CK(cudaStreamSynchronize(stream));
+                    int rc = host_allgather(hbuf.data(), hbuf.data() + Rc, sizeof(real) * (size_t)Rc);
+                    if (rc) return rc;
+                    CK(cudaMemcpyAsync(cost, hbuf.data() + (size_t)Rc * (size_t)(1 + r), sizeof(real) * (size_t)Rc, cudaMemcpyHostToDevice, stream));
+                    CK(cudaStreamSynchronize(stream));
+                }
+            }
+        } else {
             priceout_kernel<real><<<blocks, 256, 0, stream>>>(P, coef);
         }
         CK(cudaGetLastError());
@@ -825,8 +881,9 @@ struct SolverImpl final : SolverBase {
             return B2S_OK;
         }
 #ifdef B2S_WITH_NCCL
-        if (world > 1) return enqueue_pivot_sharded();
+        if (world > 1 && comm) return enqueue_pivot_sharded();
 #endif
+        if (world > 1) return fail(B2S_ERR_STATE, "sharded solve without peer memory and without NCCL");
         const long long work = std::max(Rs, ld);
         if (use_pdl) {
             // programmatic dependent launch: each kernel may be scheduled while its predecessor drains and
@@ -1108,13 +1165,13 @@ struct SolverImpl final : SolverBase {
             int rc = reset_lookahead();
             if (rc) return rc;
         }
-#ifdef B2S_WITH_NCCL
         if (p2p) {
             // a proposal prepared but not executed in phase 1 has left flags with the next pivot's number in the arenas
+            int rc = rank_barrier();   // nobody is still inside a kernel that reads them
+            if (rc) return rc;
             CK(cudaMemsetAsync(arena, 0, sizeof(ArenaHeader<real>), stream));
-            NK(ncclAllReduce(verdict, verdict, 1, ncclInt, ncclSum, comm, stream));
+            if ((rc = rank_barrier())) return rc;
         }
-#endif
         stage = kBuilt;
         return B2S_OK;
     }
@@ -1125,9 +1182,27 @@ struct SolverImpl final : SolverBase {
         CK(cudaSetDevice(dev));
         CK(cudaMemsetAsync(x_dev, 0, sizeof(double) * n, stream));
         solution_kernel<real><<<(unsigned)((m_loc + 255) / 256), 256, 0, stream>>>(P, x_dev);
+        bool reduced = world <= 1;
 #ifdef B2S_WITH_NCCL
-        if (world > 1) NK(ncclAllReduce(x_dev, x_dev, (size_t)n, ncclDouble, ncclSum, comm, stream));
+        if (!reduced && comm) {
+            NK(ncclAllReduce(x_dev, x_dev, (size_t)n, ncclDouble, ncclSum, comm, stream));
+            reduced = true;
+        }
 #endif
+        if (!reduced) {   // host layer: every entry is non-zero on at most one rank, so the sum is exact in any order
+            std::vector<double> hx((size_t)n * (size_t)(world + 1));
+            CK(cudaMemcpyAsync(hx.data(), x_dev, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, stream));
+            CK(cudaStreamSynchronize(stream));
+            int rc = host_allgather(hx.data(), hx.data() + n, sizeof(double) * (size_t)n);
+            if (rc) return rc;
+            for (int j = 0; j < n; ++j) {
+                double acc = 0.0;
+                for (int r = 0; r < world; ++r) acc += hx[(size_t)n * (size_t)(1 + r) + (size_t)j];
+                hx[(size_t)j] = acc;
+            }
+            CK(cudaMemcpyAsync(x_dev, hx.data(), sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, stream));
+            CK(cudaStreamSynchronize(stream));
+        }
         real c0;
         CK(cudaMemcpyAsync(&c0, cost, sizeof(real), cudaMemcpyDeviceToHost, stream));
         if (x) CK(cudaMemcpyAsync(x, x_dev, sizeof(double) * n, cudaMemcpyDeviceToHost, stream));
@@ -1501,6 +1576,26 @@ struct SolverImpl final : SolverBase {
         return B2S_OK;
     }
 
+    int dist_init_host(int rank_, int world_, b2s_allgather_fn fn, void* user) override
+    {
+        if (world_ < 1 || rank_ < 0 || rank_ >= world_ || world_ > kMaxPeers || (world_ > 1 && !fn))
+            return fail(B2S_ERR_ARG, "bad rank/world %d/%d (at most %d ranks) or missing all-gather callback", rank_, world_, kMaxPeers);
+        CK(cudaSetDevice(dev));
+#ifdef B2S_WITH_NCCL
+        if (comm) {
+            ncclCommDestroy(comm);
+            comm = nullptr;
+        }
+#endif
+        close_arena();
+        rank = rank_;
+        world = world_;
+        host_ag = fn;
+        host_ag_user = user;
+        free_problem();
+        return B2S_OK;
+    }
+
     int loop_info(int* launches, int* lookahead, int* persistent) override
     {
         const bool la_on = stage != kEmpty && use_lookahead();
@@ -1572,6 +1667,8 @@ struct SolverImpl final : SolverBase {
         close_arena();
         rank = rank_;
         world = world_;
+        host_ag = nullptr;
+        host_ag_user = nullptr;
         if (world > 1) {
             ncclUniqueId uid;
             static_assert(sizeof(uid) == B2S_NCCL_ID_BYTES, "unique id size");
@@ -1730,6 +1827,8 @@ int b2s_profile_lookahead(b2s_solver* s, int count, float* kernel_ms, double* st
     if (count < 1 || !kernel_ms) return B2S_ERR_ARG;
     B2S_FWD(profile_lookahead(count, kernel_ms, stage_us, pivots_done));
 }
+
+int b2s_dist_init_host(b2s_solver* s, int rank, int world, b2s_allgather_fn allgather, void* user) { B2S_FWD(dist_init_host(rank, world, allgather, user)); }
 
 int b2s_dist_unique_id(char id[B2S_NCCL_ID_BYTES])
 {

@@ -219,6 +219,19 @@ class Solver:
         return "update_kernel (fused rank-1 update + cost update + entering tournament)"
 
     # ---- sharding --------------------------------------------------------------------------------
+    def dist_init_host(self, rank, world, allgather):
+        """Bootstrap the sharded solver through a host all-gather instead of NCCL.  `allgather(send_ptr, recv_ptr, nbytes)`
+        works on raw host addresses and returns 0; it is called collectively by the library (b2s_allgather_fn)."""
+        def _cb(user, send, recv, nbytes):
+            try:
+                return int(allgather(send, recv, nbytes))
+            except Exception:   # never let an exception cross the C boundary
+                import traceback
+                traceback.print_exc()
+                return 1
+        self._host_ag = L.ALLGATHER_FN(_cb)   # keep the trampoline alive as long as the handle
+        self._ck(self.lib.b2s_dist_init_host(self.h, rank, world, C.cast(self._host_ag, C.c_void_p), None))
+
     def dist_init(self, rank, world, unique_id):
         assert len(unique_id) == L.NCCL_ID_BYTES
         self._ck(self.lib.b2s_dist_init(self.h, rank, world, unique_id))
