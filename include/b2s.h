@@ -82,7 +82,15 @@ typedef struct b2s_options {
                              (entering column, ratio test, pivot-constraint gather; sharded: both exchanges over NVLink peer
                              memory) under the stream, replacing the reference's serial chain src/solver.cu:86-105;
                              0: three launches per pivot (ratio, gather, update).  Results are bit-identical.            */
-    int reserved[4];
+    int fp64_polish;      /* fp32 solves only (the reference has none): 1 (default) = after phase 2, x_B = B^-1 b and the objective
+                             c_B.x_B are recomputed in fp64 for the final basis by iterative refinement against the fp64 problem
+                             data, with the fp32 tableau's slack block as approximate inverse; 0 = report the fp32 tableau's own
+                             values.  Single-GPU solves.                                                                     */
+    int drive_out_artificials; /* 0 (default): the reference's behaviour -- DEGENERATE when an artificial variable is still basic after
+                             a feasible phase 1 (src/twoPhaseMethod.cu:206-223, :274-282); 1: pivot such artificials out (lowest-index
+                             structural/slack column with |a| >= 1e-9 in that constraint; a constraint with none is redundant and
+                             keeps its artificial at zero) and carry on into phase 2.  Single-GPU solves.                    */
+    int reserved[2];
 } b2s_options;
 
 typedef struct b2s_stats {

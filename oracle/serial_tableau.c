@@ -161,6 +161,7 @@ typedef struct {
     int last_q, last_p;
     double last_cq;
     int relative_infeasibility; /* opt-in, not reference behaviour: see orc_phase1_verdict */
+    int drive_out;              /* opt-in, not reference behaviour: see orc_drive_out_artificials */
     double cost0_phase1_start;  /* cost[0] right after the phase-1 price-out = -(sum of |b_i|) */
 } orc_t;
 
@@ -243,7 +244,7 @@ void orc_priceout(orc_t *o)
     const int m = o->m;
     double *coef = o->s;
     for (int i = 0; i < m; ++i)
-        coef[i] = o->cost[1 + o->base[i]];
+        coef[i] = (1 + (long)o->base[i] < o->R) ? o->cost[1 + o->base[i]] : 0.0; /* (a redundant constraint's artificial, drive-out mode) */
     for (long y = 0; y < o->R; ++y) {
         const double *row = o->T + (size_t)y * m;
         double acc = o->cost[y];
@@ -281,6 +282,47 @@ static void trace_push(orc_t *o, int q, int p)
         o->hash ^= bytes[k];
         o->hash *= 1099511628211ULL;
     }
+}
+
+/* The pivot itself once (q, p) is chosen: src/solver.cu:105 (basis), :24-32/:62-66 (gather), :34-46 (rank-1 update),
+ * :48-56 (cost update).  o->col holds the entering column. */
+static void apply_pivot(orc_t *o, int q, int p, double cq)
+{
+    const int m = o->m;
+    const long R = o->R;
+    o->base[p] = q; /* src/solver.cu:105 */
+
+    /* --- gather pivot constraint (raw), src/solver.cu:24-32, :62-66 -------------------------- */
+    for (long r = 0; r < R; ++r)
+        o->rowp[r] = o->T[(size_t)r * m + p];
+    const double piv = o->col[p];
+    for (int i = 0; i < m; ++i)
+        o->s[i] = (-o->col[i]) / piv; /* :43 quotient rounded before the FMA */
+    const double sc = (-cq) / piv;    /* :54 */
+
+    /* --- rank-1 update :34-46 and cost update :48-56 --------------------------------------- */
+    const double *s = o->s;
+    double *T = o->T;
+    const double *rowp = o->rowp;
+#ifdef _OPENMP
+#pragma omp parallel for num_threads(o->threads) schedule(static)
+#endif
+    for (long r = 0; r < R; ++r) {
+        double *row = T + (size_t)r * m;
+        const double a = rowp[r];
+        const double keep = row[p] / piv;
+        for (int i = 0; i < m; ++i)
+            row[i] = fma(s[i], a, row[i]);
+        row[p] = keep;
+    }
+    for (long r = 0; r < R; ++r)
+        o->cost[r] = fma(sc, rowp[r], o->cost[r]);
+
+    o->last_q = q;
+    o->last_p = p;
+    o->last_cq = cq;
+    o->pivots[o->phase == 2 ? 1 : 0]++;
+    trace_push(o, q, p);
 }
 
 /* One iteration.  src/solver.cu:78-126 (select, unbounded test, ratio test, base update) and
@@ -350,39 +392,7 @@ int orc_pivot(orc_t *o)
     }
     if (p < 0)
         return ORC_UNBOUNDED; /* cannot happen after the max test; defensive */
-    o->base[p] = q; /* src/solver.cu:105 */
-
-    /* --- gather pivot constraint (raw), src/solver.cu:24-32, :62-66 -------------------------- */
-    for (long r = 0; r < R; ++r)
-        o->rowp[r] = o->T[(size_t)r * m + p];
-    const double piv = o->col[p];
-    for (int i = 0; i < m; ++i)
-        o->s[i] = (-o->col[i]) / piv; /* :43 quotient rounded before the FMA */
-    const double sc = (-cq) / piv;    /* :54 */
-
-    /* --- rank-1 update :34-46 and cost update :48-56 --------------------------------------- */
-    const double *s = o->s;
-    double *T = o->T;
-    const double *rowp = o->rowp;
-#ifdef _OPENMP
-#pragma omp parallel for num_threads(o->threads) schedule(static)
-#endif
-    for (long r = 0; r < R; ++r) {
-        double *row = T + (size_t)r * m;
-        const double a = rowp[r];
-        const double keep = row[p] / piv;
-        for (int i = 0; i < m; ++i)
-            row[i] = fma(s[i], a, row[i]);
-        row[p] = keep;
-    }
-    for (long r = 0; r < R; ++r)
-        o->cost[r] = fma(sc, rowp[r], o->cost[r]);
-
-    o->last_q = q;
-    o->last_p = p;
-    o->last_cq = cq;
-    o->pivots[o->phase == 2 ? 1 : 0]++;
-    trace_push(o, q, p);
+    apply_pivot(o, q, p, cq);
     return ORC_CONTINUE;
 }
 
@@ -395,6 +405,37 @@ int orc_iterate(orc_t *o, long budget)
             --budget;
     return st;
 }
+
+/* Beyond the reference (opt-in): where the reference stops with DEGENERATE because an artificial variable is
+ * still basic after a feasible phase 1 (src/twoPhaseMethod.cu:206-223, :274-282), pivot it out.  Constraints in ascending
+ * order; for constraint i with an artificial basic variable take the LOWEST-index structural or slack variable j whose entry
+ * in that constraint is non-zero by the reference's own threshold (|a_ij| >= 1e-9) and pivot on (j, i) -- a degenerate pivot,
+ * the artificial sits at level 0.  A constraint with no such entry is redundant: its artificial stays basic at zero and can
+ * never be chosen again (its row is zero on every column that survives into phase 2).  Returns the number of pivots made. */
+long orc_drive_out_artificials(orc_t *o)
+{
+    const int n = o->n, m = o->m;
+    long made = 0;
+    for (int i = 0; i < m; ++i) {
+        if (o->base[i] < n + m)
+            continue;
+        int q = -1;
+        for (int j = 0; j < n + m; ++j)
+            if (cmp3(fabs(o->T[(size_t)(1 + j) * m + i]), 0.0) > 0) {
+                q = j;
+                break;
+            }
+        if (q < 0)
+            continue; /* redundant constraint */
+        const double *qrow = o->T + (size_t)(1 + q) * m;
+        for (int k = 0; k < m; ++k)
+            o->col[k] = qrow[k];
+        apply_pivot(o, q, i, o->cost[1 + q]);
+        ++made;
+    }
+    return made;
+}
+void orc_set_drive_out(orc_t *o, int on) { o->drive_out = on; }
 
 /* src/twoPhaseMethod.cu:258-282 (:265-268 infeasible test on cost[0], :206-223 degeneracy). */
 int orc_phase1_verdict(const orc_t *o)
@@ -410,8 +451,14 @@ int orc_phase1_verdict(const orc_t *o)
         return ORC_INFEASIBLE;
     const int lo = o->n + o->m, hi = o->n + 2 * o->m;
     for (int i = 0; i < o->m; ++i)
-        if (o->base[i] >= lo && o->base[i] < hi)
-            return ORC_DEGENERATE;
+        if (o->base[i] >= lo && o->base[i] < hi) {
+            if (!o->drive_out)
+                return ORC_DEGENERATE;
+            /* opt-in mode, after orc_drive_out_artificials: an artificial may only remain in a redundant constraint */
+            for (int j = 0; j < lo; ++j)
+                if (cmp3(fabs(o->T[(size_t)(1 + j) * o->m + i]), 0.0) > 0)
+                    return ORC_DEGENERATE;
+        }
     return ORC_FEASIBLE;
 }
 
@@ -447,6 +494,10 @@ int orc_two_phase(orc_t *o, long max_pivots, double *x, double *obj)
     if (st == ORC_CONTINUE)
         return ORC_ITER_LIMIT;
     st = orc_phase1_verdict(o); /* the phase-1 solve status is ignored: :258 */
+    if (st == ORC_DEGENERATE && o->drive_out) { /* opt-in: pivot the basic artificials out instead of stopping */
+        orc_drive_out_artificials(o);
+        st = orc_phase1_verdict(o);
+    }
     if (st != ORC_FEASIBLE)
         return st;
     orc_switch_phase2(o);

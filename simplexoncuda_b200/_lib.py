@@ -27,7 +27,7 @@ class Options(C.Structure):
                 ("fold_artificials", C.c_int), ("skip_zero_rows", C.c_int), ("use_graph", C.c_int),
                 ("batch", C.c_int), ("max_pivots", C.c_longlong), ("trace_capacity", C.c_longlong),
                 ("update_variant", C.c_int), ("persistent", C.c_int), ("relative_infeasibility", C.c_int), ("lookahead", C.c_int),
-                ("reserved", C.c_int * 4)]
+                ("fp64_polish", C.c_int), ("drive_out_artificials", C.c_int), ("reserved", C.c_int * 2)]
 
 
 class Stats(C.Structure):

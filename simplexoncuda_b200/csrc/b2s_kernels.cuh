@@ -498,7 +498,10 @@ template <typename real>
 __global__ void __launch_bounds__(256) coef_kernel(PivotParams<real> P, real* coef)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < P.m_loc) coef[i] = P.cost[1 + P.base[P.col0 + i]];  // src/gaussian.cu:119-127
+    if (i < P.m_loc) {
+        const long long j = 1 + (long long)P.base[P.col0 + i];   // src/gaussian.cu:119-127
+        coef[i] = j < P.Rc ? P.cost[j] : (real)0;                 // (drive-out mode: a redundant constraint's artificial in phase 2)
+    }
 }
 
 template <typename real>
@@ -687,6 +690,130 @@ __global__ void __launch_bounds__(256) widen_rows(double* dst, long long dst_ld,
         const long long r = t / cols, c = t % cols;
         dst[r * dst_ld + c] = (double)src[r * src_ld + c];
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Driving artificial variables out of the basis (opt-in, beyond the reference: it stops with DEGENERATE at
+// src/twoPhaseMethod.cu:206-223, :274-282).  find: lowest-index structural/slack variable with a non-zero entry
+// (|a| >= 1e-9, the reference's own threshold) in constraint i; setup: make (q, i) the current pivot for the ordinary
+// gather + update kernels.
+// ---------------------------------------------------------------------------------------------
+template <typename real>
+__global__ void __launch_bounds__(256) driveout_find_kernel(PivotParams<real> P, int i, int* out)
+{
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < (long long)P.n + P.m && cmp3(fabs((double)P.T[(1 + j) * P.ld + i]), 0.0) > 0) atomicMin(out, (int)j);
+}
+template <typename real>
+__global__ void __launch_bounds__(256) driveout_setup_kernel(PivotParams<real> P, int q, int p)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < P.m_loc) P.col[t] = P.T[(1 + (long long)q) * P.ld + t];   // entering column snapshot (src/solver.cu:90-94)
+    if (t == 0) {
+        DevState* st = P.st;
+        st->q = q;
+        st->cq = (double)P.cost[1 + q];
+        st->p = p;
+        P.base[p] = q;
+        const long long k = st->pivots;
+        if (k < P.trace_cap) P.trace[k] = make_int2(q, p);
+        unsigned long long h = st->hash;
+        const unsigned int words[2] = {(unsigned)q, (unsigned)p};
+        for (int wd = 0; wd < 2; ++wd)
+            for (int by = 0; by < 4; ++by) {
+                h ^= (words[wd] >> (8 * by)) & 0xffu;
+                h *= 1099511628211ULL;
+            }
+        st->hash = h;
+        st->pivots = k + 1;
+        st->limit = k + 1;
+        st->status = kRunning;
+        st->live = 1;
+    }
+}
+// In drive-out mode an artificial may stay basic in a redundant constraint: out[1] counts only the non-redundant ones.
+template <typename real>
+__global__ void __launch_bounds__(256) driveout_verdict_kernel(PivotParams<real> P, int* out)
+{
+    const int i = blockIdx.x;   // one block per constraint
+    const int v = P.base[i];
+    if (!(v >= P.n + P.m && v < P.n + 2 * P.m)) return;
+    int any = 0;
+    for (long long j = threadIdx.x; j < (long long)P.n + P.m; j += blockDim.x)
+        any |= cmp3(fabs((double)P.T[(1 + j) * P.ld + i]), 0.0) > 0;
+    any = __syncthreads_or(any);
+    if (threadIdx.x == 0 && any) atomicAdd(out + 1, 1);
+}
+
+// ---------------------------------------------------------------------------------------------
+// fp64 polish of an fp32 solve (no reference counterpart: the reference is fp64 only, include/macro.h:6).
+// The final fp32 tableau holds an approximate inverse of the optimal basis in its slack rows
+// (T[1+n+k][i] ~ (B^-1)[i][k] for the ORIGINAL system [A | I]); iterative refinement against the fp64 problem data
+//     r = b - B x_B,   x_B += B^-1_fp32 r
+// recovers x_B = B^-1 b (and with it the objective c_B . x_B) to fp64 accuracy whenever the fp32 inverse is good to
+// better than 100 %.  orig = [ b (m) | A, variable-major (n x m) | c (n) ] in fp64.
+// ---------------------------------------------------------------------------------------------
+template <typename real>
+__global__ void __launch_bounds__(256) polish_init_kernel(PivotParams<real> P, double* xB)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < P.m) xB[i] = (double)P.T[i];   // row 0 of the fp32 tableau: its own estimate of x_B
+}
+// r[k] = b[k] - sum_i B[k][i] * xB[i];   B[:, i] = A[v_i][:] for a structural basic variable v_i, e_(v_i - n) for a slack
+template <typename real>
+__global__ void __launch_bounds__(256) polish_residual_kernel(PivotParams<real> P, const double* __restrict__ orig,
+                                                             const double* __restrict__ xB, double* r)
+{
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= P.m) return;
+    const double* A = orig + P.m;
+    double acc = orig[k];
+    for (int i = 0; i < P.m; ++i) {
+        const int v = P.base[i];
+        if (v < P.n)
+            acc = __fma_rn(-A[(long long)v * P.m + k], xB[i], acc);
+        else if (v - P.n == k)
+            acc -= xB[i];
+    }
+    r[k] = acc;
+}
+// xB[i] += sum_k T[1+n+k][i] * r[k]; also reports max |dx| and max |x| (as ordered-int bit patterns via atomicMax)
+template <typename real>
+__global__ void __launch_bounds__(256) polish_correct_kernel(PivotParams<real> P, const double* __restrict__ r, double* xB,
+                                                            unsigned long long* norms)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.m) return;
+    const real* S0 = P.T + (1 + (long long)P.n) * P.ld + i;
+    double acc = 0.0;
+    for (int k = 0; k < P.m; ++k) acc = __fma_rn((double)S0[(long long)k * P.ld], r[k], acc);
+    const double x = xB[i] + acc;
+    xB[i] = x;
+    atomicMax(norms + 0, (unsigned long long)__double_as_longlong(fabs(acc)));   // non-negative doubles order like integers
+    atomicMax(norms + 1, (unsigned long long)__double_as_longlong(fabs(x)));
+}
+// x[v_i] = xB[i] for structural basics; objective = sum c[v_i] * xB[i] in ascending i (one block, deterministic)
+template <typename real>
+__global__ void __launch_bounds__(kSelBlock) polish_finish_kernel(PivotParams<real> P, const double* __restrict__ orig,
+                                                                 const double* __restrict__ xB, double* x, double* obj)
+{
+    __shared__ double part[kSelBlock];
+    const double* c = orig + P.m + (long long)P.n * P.m;
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < P.m; i += kSelBlock) {
+        const int v = P.base[i];
+        if (v < P.n) {
+            x[v] = xB[i];
+            acc = __fma_rn(c[v], xB[i], acc);
+        }
+    }
+    part[threadIdx.x] = acc;
+    __syncthreads();
+    for (int off = kSelBlock / 2; off > 0; off >>= 1) {
+        if ((int)threadIdx.x < off) part[threadIdx.x] += part[threadIdx.x + off];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *obj = part[0];
 }
 
 }  // namespace b2s

@@ -136,6 +136,10 @@ struct SolverImpl final : SolverBase {
     int *base = nullptr, *neg = nullptr, *verdict = nullptr;
     double* x_dev = nullptr;
     double* stage_dev = nullptr;  // fp64 staging for fp32 loads / exports
+    double* orig64 = nullptr;     // fp32 solves: the problem in fp64 ([b | A | c]) for the final polish
+    size_t cap_orig = 0;
+    bool have_orig = false;
+    double polish_residual = -1.0; // last polish: max |dx| / max |x| of the final refinement step
     size_t cap_stage = 0;
     DevState* st = nullptr;
     DevState* st_host = nullptr;  // pinned, [0] = current snapshot, [1..2] = pipelined poll slots
@@ -242,6 +246,10 @@ struct SolverImpl final : SolverBase {
         cudaFree(neg);
         cudaFree(x_dev);
         cudaFree(stage_dev);
+        cudaFree(orig64);
+        orig64 = nullptr;
+        cap_orig = 0;
+        have_orig = false;
         cudaFree(tile_rec);
         cudaFree(col2);
         cudaFree(s2);
@@ -707,6 +715,7 @@ struct SolverImpl final : SolverBase {
             CK(cudaMemcpyAsync(cst, c, sizeof(double) * n, cudaMemcpyHostToDevice, stream));
             convert_rows<<<1024, 256, 0, stream>>>(T, ld, stage_dev, (long long)m_loc, (long long)(n + 1), m_loc);
             convert_rows<<<64, 256, 0, stream>>>(c_dev, (long long)n, cst, (long long)n, 1ll, n);
+            if ((rc = keep_original_from_stage())) return rc;
         }
         CK(cudaStreamSynchronize(stream));
         stage = kLoaded;
@@ -748,9 +757,86 @@ struct SolverImpl final : SolverBase {
             generate_matrix_kernel<real><<<grid, 256, 0, stream>>>(T, ld, 1ll, n, m_loc, col0, seeds[2], lo, span, jump_tables);
         }
         CK(cudaGetLastError());
+        if (sizeof(real) != sizeof(double) && (rc = keep_original_from_tableau())) return rc;
         CK(cudaStreamSynchronize(stream));
         stage = kLoaded;
         sec_load = now_s() - t0;
+        return B2S_OK;
+    }
+
+    // fp32 solves keep the problem in fp64 for the final polish (single GPU; the sharded path returns the plain fp32 answer)
+    int ensure_orig()
+    {
+        have_orig = false;
+        if (sizeof(real) == sizeof(double) || world > 1 || !opt.fp64_polish) return B2S_OK;
+        const size_t need = (size_t)(n + 1) * (size_t)m + (size_t)n;
+        if (need > cap_orig) {
+            cudaFree(orig64);
+            orig64 = nullptr;
+            cap_orig = 0;
+            if (cudaMalloc(&orig64, sizeof(double) * need) != cudaSuccess) {
+                cudaGetLastError();
+                return B2S_OK;   // no room for the copy: solve without polish
+            }
+            cap_orig = need;
+        }
+        have_orig = true;
+        return B2S_OK;
+    }
+    int keep_original_from_stage()   // stage_dev = [b | A | c] in fp64, exactly what the caller passed
+    {
+        int rc = ensure_orig();
+        if (rc || !have_orig) return rc;
+        CK(cudaMemcpyAsync(orig64, stage_dev, sizeof(double) * ((size_t)(n + 1) * (size_t)m + (size_t)n), cudaMemcpyDeviceToDevice, stream));
+        return B2S_OK;
+    }
+    int keep_original_from_tableau()  // generated in working precision: the fp64 problem is the widened one
+    {
+        int rc = ensure_orig();
+        if (rc || !have_orig) return rc;
+        widen_rows<<<1024, 256, 0, stream>>>(orig64, (long long)m, T, ld, (long long)(n + 1), m);
+        widen_rows<<<64, 256, 0, stream>>>(orig64 + (size_t)(n + 1) * m, (long long)n, c_dev, (long long)n, 1ll, n);
+        CK(cudaGetLastError());
+        return B2S_OK;
+    }
+
+    // Iterative refinement of x_B against the fp64 problem with the fp32 tableau's slack block as approximate inverse.
+    // Returns false (and leaves x_dev / the fp32 objective alone) if the refinement does not contract.
+    int polish_fp64(double* obj, bool* used)
+    {
+        *used = false;
+        DevBuf<double> xB, r, o;
+        DevBuf<unsigned long long> norms;
+        CK(xB.alloc((size_t)m));
+        CK(r.alloc((size_t)m));
+        CK(o.alloc(1));
+        CK(norms.alloc(2));
+        const unsigned blocks = (unsigned)((m + 255) / 256);
+        polish_init_kernel<real><<<blocks, 256, 0, stream>>>(P, xB.p);
+        double prev = -1.0, rel = 1.0;
+        for (int it = 0; it < 8; ++it) {
+            CK(cudaMemsetAsync(norms.p, 0, 2 * sizeof(unsigned long long), stream));
+            polish_residual_kernel<real><<<blocks, 256, 0, stream>>>(P, orig64, xB.p, r.p);
+            polish_correct_kernel<real><<<blocks, 256, 0, stream>>>(P, r.p, xB.p, norms.p);
+            unsigned long long hn[2];
+            CK(cudaMemcpyAsync(hn, norms.p, sizeof(hn), cudaMemcpyDeviceToHost, stream));
+            CK(cudaStreamSynchronize(stream));
+            double dx, xm;
+            memcpy(&dx, &hn[0], 8);
+            memcpy(&xm, &hn[1], 8);
+            if (!(dx == dx) || !(xm == xm)) return B2S_OK;          // NaN: give up, keep the fp32 answer
+            rel = dx / std::max(xm, 1e-300);
+            if (it >= 2 && prev >= 0 && rel > prev && rel > 1e-6) return B2S_OK;   // not contracting
+            prev = rel;
+            if (rel < 1e-15) break;
+        }
+        polish_residual = rel;
+        if (rel > 1e-9) return B2S_OK;
+        CK(cudaMemsetAsync(x_dev, 0, sizeof(double) * n, stream));
+        polish_finish_kernel<real><<<1, kSelBlock, 0, stream>>>(P, orig64, xB.p, x_dev, o.p);
+        CK(cudaMemcpyAsync(obj, o.p, sizeof(double), cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        *used = true;
         return B2S_OK;
     }
 
@@ -1125,6 +1211,44 @@ struct SolverImpl final : SolverBase {
         return fail(B2S_ERR_CUDA, "device loop stopped with undocumented status %d", s_);
     }
 
+    // Opt-in (b2s_options.drive_out_artificials): pivot the artificials that are still basic after a feasible phase 1 out of
+    // the basis, constraint by constraint, with the ordinary gather + update kernels (see driveout_*_kernel).
+    int drive_out(long long* made_out)
+    {
+        if (made_out) *made_out = 0;
+        if (world > 1) return fail(B2S_ERR_STATE, "drive_out_artificials is single-GPU only");
+        CK(cudaSetDevice(dev));
+        std::vector<int> hb((size_t)m);
+        CK(cudaMemcpyAsync(hb.data(), base, sizeof(int) * (size_t)m, cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        DevBuf<int> found;
+        CK(found.alloc(1));
+        long long made = 0;
+        const long long work = std::max(Rs, ld);
+        const unsigned fb = (unsigned)(((long long)n + m + 255) / 256);
+        for (int i = 0; i < m; ++i) {
+            if (hb[(size_t)i] < n + m) continue;
+            const int big = INT_MAX;
+            CK(cudaMemcpyAsync(found.p, &big, sizeof(int), cudaMemcpyHostToDevice, stream));
+            driveout_find_kernel<real><<<fb, 256, 0, stream>>>(P, i, found.p);
+            int q = INT_MAX;
+            CK(cudaMemcpyAsync(&q, found.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+            CK(cudaStreamSynchronize(stream));
+            if (q == INT_MAX) continue;   // redundant constraint: its artificial stays basic at zero
+            int rc = reset_tickets();
+            if (rc) return rc;
+            driveout_setup_kernel<real><<<(unsigned)((m_loc + 255) / 256), 256, 0, stream>>>(P, q, i);
+            gather_kernel<real, false><<<(unsigned)((work + 255) / 256), 256, 0, stream>>>(P);
+            update_fn()<<<upd_grid, kSelBlock, upd_smem, stream>>>(P);
+            CK(cudaGetLastError());
+            ++made;
+        }
+        CK(cudaStreamSynchronize(stream));
+        pivots_p1 += made;
+        if (made_out) *made_out = made;
+        return B2S_OK;
+    }
+
     int phase1_verdict(int* status) override
     {
         if (phase != 1 || (stage != kReady && stage != kPhaseDone))
@@ -1143,6 +1267,16 @@ struct SolverImpl final : SolverBase {
             CK(cudaStreamSynchronize(stream));
             const double scale = std::max(1.0, std::fabs(cost0_phase1_start));
             h[0] = ((double)c0 < -1e-9 * scale) ? 1 : 0;
+        }
+        if (opt.drive_out_artificials && world == 1 && h[0] == 0 && h[1] > 0) {
+            // beyond the reference: pivot the basic artificials out; what may remain sits in redundant constraints
+            long long made = 0;
+            int rc = drive_out(&made);
+            if (rc) return rc;
+            CK(cudaMemsetAsync(verdict, 0, 2 * sizeof(int), stream));
+            driveout_verdict_kernel<real><<<(unsigned)m, 256, 0, stream>>>(P, verdict);
+            CK(cudaMemcpyAsync(h, verdict, sizeof(h), cudaMemcpyDeviceToHost, stream));
+            CK(cudaStreamSynchronize(stream));
         }
         *status = h[0] ? B2S_INFEASIBLE : (h[1] > 0 ? B2S_DEGENERATE : B2S_FEASIBLE);
         return B2S_OK;
@@ -1205,9 +1339,18 @@ struct SolverImpl final : SolverBase {
         }
         real c0;
         CK(cudaMemcpyAsync(&c0, cost, sizeof(real), cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        double objective = (double)c0;
+        if (sizeof(real) != sizeof(double) && have_orig && phase == 2 && world == 1) {
+            bool used = false;
+            double polished = 0.0;
+            int rc = polish_fp64(&polished, &used);   // rewrites x_dev on success
+            if (rc) return rc;
+            if (used) objective = polished;
+        }
         if (x) CK(cudaMemcpyAsync(x, x_dev, sizeof(double) * n, cudaMemcpyDeviceToHost, stream));
         CK(cudaStreamSynchronize(stream));
-        if (obj) *obj = (double)c0;
+        if (obj) *obj = objective;
         return B2S_OK;
     }
 
@@ -1715,6 +1858,8 @@ void b2s_default_options(b2s_options* opt)
     opt->update_variant = 8;
     opt->persistent = 2;
     opt->lookahead = 2;
+    opt->fp64_polish = 1;
+    opt->drive_out_artificials = 0;
 }
 
 int b2s_device_count(void)

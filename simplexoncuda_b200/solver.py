@@ -30,7 +30,7 @@ class Solver:
 
     def __init__(self, device=0, dtype=L.F64, pivot_rule=L.RULE_REFERENCE, fold_artificials=True,
                  skip_zero_rows=True, use_graph=True, batch=0, max_pivots=0, trace_capacity=0,
-                 update_variant=8, persistent="auto", relative_infeasibility=False, lookahead="auto"):
+                 update_variant=8, persistent="auto", relative_infeasibility=False, lookahead="auto", fp64_polish=True, drive_out_artificials=False):
         self.lib = L.load()
         opt = L.Options()
         self.lib.b2s_default_options(C.byref(opt))
@@ -47,6 +47,8 @@ class Solver:
         opt.persistent = 2 if persistent in ("auto", None) else int(bool(persistent))
         opt.relative_infeasibility = int(bool(relative_infeasibility))
         opt.lookahead = 2 if lookahead in ("auto", None) else int(bool(lookahead))
+        opt.fp64_polish = int(bool(fp64_polish))
+        opt.drive_out_artificials = int(bool(drive_out_artificials))
         self.h = C.c_void_p()
         rc = self.lib.b2s_create(C.byref(opt), C.byref(self.h))
         if rc != L.OK:

@@ -34,6 +34,9 @@ def lib():
         l.orc_extract.argtypes = [C.c_void_p, _dp, _dp]
         l.orc_two_phase.argtypes = [C.c_void_p, C.c_long, _dp, _dp]
         l.orc_set_relative_infeasibility.argtypes = [C.c_void_p, C.c_int]
+        l.orc_set_drive_out.argtypes = [C.c_void_p, C.c_int]
+        l.orc_drive_out_artificials.argtypes = [C.c_void_p]
+        l.orc_drive_out_artificials.restype = C.c_long
         l.orc_rows.restype = C.c_long
         l.orc_rows.argtypes = [C.c_void_p]
         l.orc_pivots.restype = C.c_long
@@ -87,7 +90,7 @@ def xorwow_outputs(seed, offset, count):
 class Oracle:
     """Stepping handle over the serial restatement."""
 
-    def __init__(self, A, b, c, rule=0, threads=1, trace_cap=1 << 20, relative_infeasibility=False):
+    def __init__(self, A, b, c, rule=0, threads=1, trace_cap=1 << 20, relative_infeasibility=False, drive_out=False):
         self.A = np.ascontiguousarray(A, dtype=np.float64)
         self.b = np.ascontiguousarray(b, dtype=np.float64)
         self.c = np.ascontiguousarray(c, dtype=np.float64)
@@ -97,6 +100,8 @@ class Oracle:
                                    self.c.ctypes.data_as(_dp), rule, threads)
         if relative_infeasibility:
             self.l.orc_set_relative_infeasibility(self.h, 1)
+        if drive_out:
+            self.l.orc_set_drive_out(self.h, 1)
         self._trace = np.zeros((trace_cap, 2), dtype=np.int32)
         self.l.orc_set_trace(self.h, self._trace.ctypes.data_as(_ip), trace_cap)
 
@@ -121,6 +126,9 @@ class Oracle:
 
     def phase1_verdict(self):
         return self.l.orc_phase1_verdict(self.h)
+
+    def drive_out_artificials(self):
+        return self.l.orc_drive_out_artificials(self.h)
 
     def switch_phase2(self):
         self.l.orc_switch_phase2(self.h)

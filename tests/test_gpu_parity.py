@@ -272,22 +272,33 @@ def test_full_size_properties(S):
 
 
 # ---- fp32 mode (no reference counterpart: the reference does not compile with TYPE=float) ----------
-@pytest.mark.parametrize("n,m,seed", [(64, 64, 3), (256, 256, 25856), (512, 256, 51456), (300, 700, 9)])
+@pytest.mark.parametrize("n,m,seed", [(64, 64, 3), (256, 256, 25856), (512, 256, 51456), (300, 700, 9), (1024, 1024, 103424)])
 def test_fp32_objective_close_to_fp64_oracle(S, n, m, seed):
-    """fp32 parity is unpinned against the reference; the bar is the north star's: same status and an
-    objective within 1e-4 relative of the fp64 oracle (the pivot path may legitimately differ)."""
+    """fp32 parity is unpinned against the reference (it cannot be built with TYPE=float); the bar is the north star's:
+    same status and an objective within 1e-4 relative of the fp64 oracle at EVERY size (the pivot path may legitimately
+    differ).  The fp32 tableau alone drifts to 5e-4 .. 6e-3 over hundreds of pivots; the fp64 polish of the final basis
+    (b2s_options.fp64_polish, on by default) brings objective and x back to the fp64 values of that basis."""
     A, b, c = O.generate(n, m, O.seed_triplet(seed, 1), 1, 100)
-    ref = O.Oracle(A, b, c).two_phase()
+    ref = O.Oracle(A, b, c, threads=4).two_phase()
     with S.Solver(dtype=S.F32, max_pivots=200000) as s:
         s.load(A, b, c)
         r = s.solve()
     assert r["status"] == ref["status"] == 0
-    # 1e-4 relative (the north star's fp32 bar) holds for small LPs; a plain fp32 tableau accumulates rounding
-    # over hundreds of pivots, so larger LPs get the looser bound recorded in DESIGN.md section 6
-    tol = 1e-4 if max(n, m) <= 64 else 5e-2
-    assert abs(r["objective"] - ref["objective"]) <= tol * abs(ref["objective"])
-    # the fp32 solution must be (nearly) feasible for the fp64 problem
-    assert np.all(A.T @ r["x"] <= b * (1 + 5e-2) + 5e-2) and np.all(r["x"] >= 0)
+    tol = 1e-4
+    assert abs(r["objective"] - ref["objective"]) <= tol * abs(ref["objective"]), (r["objective"], ref["objective"])
+    # the polished solution is feasible for the fp64 problem to fp64 accuracy, and its objective is c.x
+    assert np.all(A.T @ r["x"] <= b * (1 + 1e-9) + 1e-9) and np.all(r["x"] >= -1e-9)
+    assert abs(float(c @ r["x"]) - r["objective"]) <= 1e-9 * abs(r["objective"])
+
+
+def test_fp32_without_polish_is_the_plain_fp32_tableau(S):
+    """fp64_polish=False reports the fp32 tableau's own objective: close for a small LP, visibly off for a larger one."""
+    A, b, c = O.generate(64, 64, O.seed_triplet(3, 1), 1, 100)
+    ref = O.Oracle(A, b, c).two_phase()
+    with S.Solver(dtype=S.F32, fp64_polish=False, max_pivots=200000) as s:
+        s.load(A, b, c)
+        r = s.solve()
+    assert r["status"] == 0 and abs(r["objective"] - ref["objective"]) <= 1e-3 * abs(ref["objective"])
 
 
 def test_fp32_generator_and_examples(S):
@@ -351,6 +362,29 @@ def test_relative_infeasibility_tolerance(S, seed, n, m, scale):
     assert int(r["stats"].trace_hash) == ref["hash"] and r["objective"] == ref["objective"]
     base = O.Oracle(A, b, c).two_phase()
     assert abs(r["objective"] - base["objective"] * scale) <= 1e-9 * abs(r["objective"])
+
+
+def test_drive_out_artificials(S):
+    """LPs the reference gives up on with DEGENERATE (an artificial still basic after a feasible phase 1).  Default: the same
+    verdict (parity).  drive_out_artificials=True: pivots them out and finishes -- pivot for pivot like the oracle in the same
+    mode, and with the optimum scipy/HiGHS finds (committed in the fixture)."""
+    cases = json.load(open(os.path.join(HERE, "golden", "degenerate.json")))["cases"]
+    assert len(cases) >= 10
+    for cs in cases:
+        A, b, c = np.array(cs["A"], float), np.array(cs["b"], float), np.array(cs["c"], float)
+        assert check_solve(S, A, b, c, max_pivots=2000)["status"] == S.DEGENERATE
+        for opts in (dict(), dict(persistent=False), dict(persistent=False, lookahead=False), dict(fold_artificials=False)):
+            ref = O.Oracle(A, b, c, drive_out=True).two_phase(max_pivots=2000)
+            with S.Solver(drive_out_artificials=True, max_pivots=2000, **opts) as s:
+                s.load(A, b, c)
+                r = s.solve()
+                qp, cnt, h = s.trace()
+            assert r["status"] == ref["status"] == cs["drive_out_status"]
+            assert same(qp, ref["trace"]) and h == ref["hash"] and str(h) == cs["trace_hash"]
+            assert (r["stats"].pivots_phase1, r["stats"].pivots_phase2) == tuple(ref["pivots"])
+            if r["status"] == 0:
+                assert r["objective"] == ref["objective"] and same(r["x"], ref["x"])
+                assert abs(r["objective"] - cs["highs_objective"]) <= 1e-7 * max(1.0, abs(cs["highs_objective"]))
 
 
 # ---- degenerate shapes and data -------------------------------------------------------------------------

@@ -207,3 +207,18 @@ def test_relative_infeasibility_mode_oracle():
     p = json.load(open(os.path.join(HERE, "golden", "examples.json")))["infeasibleProblem"]["text"]
     Ai, bi, ci = parse_lp(p)
     assert O.Oracle(Ai, bi, ci, relative_infeasibility=True).two_phase()["status"] == O.INFEASIBLE
+
+
+def test_oracle_drive_out_mode_matches_highs_fixture():
+    """The oracle's opt-in drive-out mode (beyond the reference) on the committed DEGENERATE fixtures: default mode keeps the
+    reference verdict, drive-out mode reproduces the committed pivots and the optimum HiGHS found when the fixture was made."""
+    import json
+    import os
+    cases = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "degenerate.json")))["cases"]
+    for cs in cases:
+        A, b, c = np.array(cs["A"], float), np.array(cs["b"], float), np.array(cs["c"], float)
+        assert O.Oracle(A, b, c).two_phase(max_pivots=2000)["status"] == -3
+        r = O.Oracle(A, b, c, drive_out=True).two_phase(max_pivots=2000)
+        assert r["status"] == cs["drive_out_status"] and str(r["hash"]) == cs["trace_hash"] and list(r["pivots"]) == cs["pivots"]
+        if r["status"] == 0:
+            assert abs(r["objective"] - cs["highs_objective"]) <= 1e-7 * max(1.0, abs(cs["highs_objective"]))
