@@ -866,11 +866,17 @@ __device__ __noinline__ void la_chain(const PivotParams<real>& P, LaState* la, u
 // the phase-ending status the chain found (kFeasible / kUnbounded); kStatusPeerTimeout when somebody stopped publishing.
 __device__ __forceinline__ int la_finalize(LaState* la, Proposal* nxt, unsigned tseq, int H, bool live)
 {
-    if (live && __ldcg(&nxt->q_seq) != tseq) return kStatusPeerTimeout;
+    const unsigned qs = __ldcg(&nxt->q_seq);
     const int sn = __ldcg(&nxt->status_next);
+    unsigned ds[kLaMaxHelpers];
+#pragma unroll
+    for (int k = 0; k < kLaMaxHelpers; ++k) ds[k] = __ldcg(&la->done_seq[k]);   // all in flight together
+    if (live && qs != tseq) return kStatusPeerTimeout;
     if (sn != kRunning) return sn;
-    for (int k = 0; k < H; ++k)
-        if (__ldcg(&la->done_seq[k]) != tseq) return kStatusPeerTimeout;
+    bool all = true;
+#pragma unroll
+    for (int k = 0; k < kLaMaxHelpers; ++k) all = all && (k >= H || ds[k] == tseq);
+    if (!all) return kStatusPeerTimeout;
     nxt->ready_seq = tseq;
     return kRunning;
 }
@@ -891,27 +897,43 @@ __global__ void __launch_bounds__(kSelBlock, 1) update_la_kernel(const __grid_co
 
     DevState* st = P.st;
     LaState* la = P.la;
+    // One round trip for everything the kernel needs to know: the loop state and BOTH proposals are fetched together and
+    // the right generation is picked afterwards (a dependent second and third fetch would cost a microsecond each).
     const int status = __ldcg(&st->status);
     const long long pivots = __ldcg(&st->pivots), limit = __ldcg(&st->limit);
+    unsigned ready2[2];
+    int p2[2], q2[2];
+    long long nz2[2];
+    double sc2[2], piv2[2];
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+        ready2[g] = __ldcg(&la->prop[g].ready_seq);
+        p2[g] = __ldcg(&la->prop[g].p);
+        q2[g] = __ldcg(&la->prop[g].q);
+        nz2[g] = __ldcg(&la->prop[g].nz);
+        sc2[g] = __ldcg(&la->prop[g].sc);
+        piv2[g] = __ldcg(&la->prop[g].piv);
+    }
     if (status != kRunning || pivots >= limit) return;
     const unsigned seq = (unsigned)(pivots + 1);
     const int par = (int)(seq & 1u);
     const Proposal* cur = &la->prop[par];
-    if (__ldcg(&cur->ready_seq) != seq) {
+    if ((par ? ready2[1] : ready2[0]) != seq) {
         if (blockIdx.x == 0 && threadIdx.x == 0) st->status = kStatusInternal;
         return;
     }
     const int H = P.helpers;
     const bool helper = (int)blockIdx.x < H;
-    const int p = __ldcg(&cur->p), q = __ldcg(&cur->q);
+    const int p = par ? p2[1] : p2[0], q = par ? q2[1] : q2[0];
     const int lp = p - P.col0;   // outside [0, m_loc) when another rank owns the pivot column
     const real* rowp = la_rowp(P, par);
     const real* svec = P.s2 + (size_t)par * P.ld;
     const bool reverse = P.serpentine && (seq & 1u);
     const int rpp = kSelBlock >> P.log2_tpr;
     const int tile_rows = rpp * U;
-    const int nlive = (int)__ldcg(&cur->nz);
+    const int nlive = (int)(par ? nz2[1] : nz2[0]);
     const int ntiles = ((nlive + tile_rows - 1) / tile_rows) * P.nchunks;
+    const real sc_cur = (real)(par ? sc2[1] : sc2[0]), piv_cur = (real)(par ? piv2[1] : piv2[0]);
     if (blockIdx.x == 0 && threadIdx.x == 0) la->stamps[0] = globaltimer();
 
     {
@@ -919,11 +941,11 @@ __global__ void __launch_bounds__(kSelBlock, 1) update_la_kernel(const __grid_co
         const int first = ((int)gridDim.x > H) ? H : 0;
         const int ncta = (int)gridDim.x - first;
         if ((int)blockIdx.x >= first && (int)blockIdx.x - first < P.Gc)
-            la_cost_blocks<real>(P, la, &la->prop[par ^ 1], seq + 1u, rowp, (real)__ldcg(&cur->sc), first, ncta,
+            la_cost_blocks<real>(P, la, &la->prop[par ^ 1], seq + 1u, rowp, sc_cur, first, ncta,
                                  P.rowpos + (size_t)par * P.rowp_stride, tile_rows, sm, sh);
     }
     if (helper)
-        la_chain<real, true>(P, la, seq, (int)blockIdx.x, H, rowp, svec, (real)__ldcg(&cur->piv), (long long)lp, p, q, reverse,
+        la_chain<real, true>(P, la, seq, (int)blockIdx.x, H, rowp, svec, piv_cur, (long long)lp, p, q, reverse,
                              (long long)ntiles, sm, smax, sh);
 
     // ---- streaming ---------------------------------------------------------------------------------------
@@ -1020,7 +1042,7 @@ __global__ void __launch_bounds__(kSelBlock, 1) update_la_kernel(const __grid_co
                 }
             if (lp >= c && lp < c + EPT) {
                 // the thread that owns the pivot column overwrites its entries with a_pr / pivot (src/solver.cu:43)
-                const real pv = (real)__ldcg(&cur->piv);
+                const real pv = (real)__ldcg(&cur->piv);   // (rare path: re-read rather than keep a register alive through the loop)
 #pragma unroll 1
                 for (int u = 0; u < U; ++u) {
                     const int r = ts.row[buf][ty + u * rpp];

@@ -930,7 +930,7 @@ struct SolverImpl final : SolverBase {
             priceout_kernel<real><<<blocks, 256, 0, stream>>>(P, coef);
         }
         CK(cudaGetLastError());
-        if (phase == 1 && opt.relative_infeasibility) {  // magnitude the phase-1 objective starts from: -(sum |b_i|)
+        if (phase == 1 && (opt.relative_infeasibility || sizeof(real) != sizeof(double))) {  // magnitude the phase-1 objective starts from: -(sum |b_i|)
             real c0 = 0;
             CK(cudaMemcpyAsync(&c0, cost, sizeof(real), cudaMemcpyDeviceToHost, stream));
             CK(cudaStreamSynchronize(stream));
@@ -1267,6 +1267,17 @@ struct SolverImpl final : SolverBase {
             CK(cudaStreamSynchronize(stream));
             const double scale = std::max(1.0, std::fabs(cost0_phase1_start));
             h[0] = ((double)c0 < -1e-9 * scale) ? 1 : 0;
+        }
+        if (sizeof(real) != sizeof(double)) {
+            // fp32 (no reference counterpart): the absolute -1e-9 test is below fp32 resolution -- after ~m pivots the phase-1
+            // objective carries a residual of order 1e-6 x its starting magnitude.  With no artificial variable left in the basis
+            // the phase-1 optimum is exactly 0 whatever the accumulated residual says; otherwise the residual is judged against
+            // fp32 resolution.
+            real c0 = 0;
+            CK(cudaMemcpyAsync(&c0, cost, sizeof(real), cudaMemcpyDeviceToHost, stream));
+            CK(cudaStreamSynchronize(stream));
+            const double scale = std::max(1.0, std::fabs(cost0_phase1_start));
+            h[0] = (h[1] > 0 && (double)c0 < -1e-5 * scale) ? 1 : 0;
         }
         if (opt.drive_out_artificials && world == 1 && h[0] == 0 && h[1] > 0) {
             // beyond the reference: pivot the basic artificials out; what may remain sits in redundant constraints
