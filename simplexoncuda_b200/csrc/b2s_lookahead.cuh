@@ -897,6 +897,11 @@ __global__ void __launch_bounds__(kSelBlock, 1) update_la_kernel(const __grid_co
 
     DevState* st = P.st;
     LaState* la = P.la;
+    // Programmatic dependent launch: this grid may have been scheduled while the previous pivot's grid was draining; nothing
+    // may be read before that grid has completed.  Let the next pivot's grid be scheduled behind this one right away -- its
+    // CTAs take the SMs as ours leave and wait here.
+    pdl_wait();
+    pdl_trigger();
     // One round trip for everything the kernel needs to know: the loop state and BOTH proposals are fetched together and
     // the right generation is picked afterwards (a dependent second and third fetch would cost a microsecond each).
     const int status = __ldcg(&st->status);

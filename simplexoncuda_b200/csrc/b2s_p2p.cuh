@@ -78,7 +78,9 @@ __global__ void __launch_bounds__(kSelBlock) ratio_p2p_kernel(PivotParams<real> 
     c.k = -1;
     real mx = Limits<real>::tiny();
     {
-        const long long gi = (long long)gb * kSelBlock + threadIdx.x;  // sharded: m <= 512*1024, one element per thread
+        // one element per thread: prepare() refuses sharded problems with more than kSelBlock * kMaxSlots constraints, so the
+        // Gm_loc CTAs launched here cover the slab exactly once (b2s_solver.cu, prepare)
+        const long long gi = (long long)gb * kSelBlock + threadIdx.x;
         if (gi < P.m) {
             const long long li = gi - P.col0;
             const real a = qrow[li];

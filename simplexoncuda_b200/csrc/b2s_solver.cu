@@ -158,6 +158,7 @@ struct SolverImpl final : SolverBase {
     int *rowlist = nullptr, *rowpos = nullptr;
     int la_grid = 0;
     int la_u = 8;
+    bool la_pdl = false;  // programmatic dependent launch between consecutive pivots: measured, no gain (profiles/r02_lookahead.md)
     int la_helpers = 0;   // 0 = default: 8 on one GPU (chain hidden anyway), 16 when sharded (the chain is the critical path)
     long long wait_cycles = 4000000000ll;
     int fault_rank = -1;
@@ -285,6 +286,7 @@ struct SolverImpl final : SolverBase {
         CK(cudaMalloc(&la, sizeof(LaState)));
         CK(cudaMemsetAsync(la, 0, sizeof(LaState), stream));
         if (const char* e = getenv("B2S_LA_U")) la_u = atoi(e) == 4 ? 4 : 8;
+        if (const char* e = getenv("B2S_LA_PDL")) la_pdl = atoi(e) != 0;
         if (const char* e = getenv("B2S_LA_HELPERS")) la_helpers = std::max(1, std::min(kLaMaxHelpers, atoi(e)));
         if (const char* e = getenv("B2S_PEER_TIMEOUT_MS")) wait_cycles = std::max(1ll, atoll(e)) * 2000000ll;  // ~2 GHz
         if (const char* e = getenv("B2S_FAULT_RANK")) fault_rank = atoi(e);
@@ -521,6 +523,10 @@ struct SolverImpl final : SolverBase {
         if (const char* e = getenv("B2S_LOOKAHEAD")) mode = atoi(e);
         if (mode == 0 || use_persistent() || variant_index() != 8) return false;
         if (world > 1 && !p2p) return false;
+        // auto: the chain takes ~30 us even on an idle memory system (profiles/r02_lookahead.md); on one GPU it only pays once a
+        // pivot streams longer than that, i.e. from ~280 MB of stored tableau (measured crossover, r02_loop_mode_sweep).  Sharded
+        // solves always gain: the chain replaces two exposed NVLink exchanges and three extra launches.
+        if (mode == 2 && world == 1 && (double)Rs * (double)ld * sizeof(real) < 280e6) return false;
         if ((long long)m > (long long)kSelBlock * kMaxSlots) return false;          // one ratio element per helper thread
         if (R1 >= (long long)kRowMask - 1 || ld >= (long long)kNoColumn - 1) return false;  // ticket-word fields
         return true;
@@ -955,8 +961,7 @@ struct SolverImpl final : SolverBase {
     {
         if (use_lookahead()) {
             // one launch per pivot: streaming update + the next pivot's selection (and, sharded, its two exchanges) under it
-            la_fn()<<<la_grid, kSelBlock, 0, stream>>>(P);
-            return B2S_OK;
+            return launch_la();
         }
         if (world > 1 && p2p) {
             // exchanges done by the kernels themselves over NVLink peer memory (b2s_p2p.cuh)
@@ -983,6 +988,16 @@ struct SolverImpl final : SolverBase {
         gather_kernel<real, false><<<(unsigned)((work + 255) / 256), 256, 0, stream>>>(P);
         update_fn()<<<upd_grid, kSelBlock, upd_smem, stream>>>(P);
         return B2S_OK;
+    }
+
+    // The look-ahead kernel; B2S_LA_PDL=1 adds programmatic stream serialization between consecutive pivots (measured: no gain).
+    int launch_la()
+    {
+        if (!la_pdl) {
+            la_fn()<<<la_grid, kSelBlock, 0, stream>>>(P);
+            return B2S_OK;
+        }
+        return launch_pdl((const void*)la_fn(), (unsigned)la_grid, kSelBlock);
     }
 
     int launch_pdl(const void* fn, unsigned grid, unsigned block)
@@ -1782,7 +1797,7 @@ struct SolverImpl final : SolverBase {
         long long made = 0;
         for (int k = 0; k < count; ++k) {
             CK(cudaEventRecord(ev[2 * k], stream));
-            la_fn()<<<la_grid, kSelBlock, 0, stream>>>(P);
+            if ((rc = launch_la())) return rc;
             CK(cudaEventRecord(ev[2 * k + 1], stream));
             if (stage_us) {   // the stamps are per pivot: read them before the next launch overwrites them
                 CK(cudaMemcpyAsync(&snap[(size_t)k], la, sizeof(LaState), cudaMemcpyDeviceToHost, stream));
