@@ -20,19 +20,29 @@
 // exposed exchange.
 //
 // Hazard protocol (the streaming CTAs overwrite the tableau in place while the helpers read it):
-//   * row 0 (RHS) is never touched by the streaming CTAs; the helpers update it.
-//   * Tiles are handed out by ONE 64-bit atomic word: [ticket count | published row | published column].
-//     A helper publishes the entering variable's row (later: the next pivot column) by adding it into that
-//     word; the value the atomic returns is the number of tiles claimed before the publication.  A CTA that
-//     claims a tile learns, from the same atomic that gives it the tile, which publications preceded its
-//     claim -- single-location coherence order, no fences.  It then leaves the published row / column
-//     untouched ("held old"); the helpers compute those elements themselves from the old values.
-//   * Tiles claimed BEFORE a publication are updated in full; the helpers wait for the tile's completion
-//     record and read the new values.
-//   * The next pivot column may thus stay stale in the tableau.  It is never read: during the next pivot
-//     its raw values ARE the gathered vector rowp', and the streaming loop overwrites the column with
-//     rowp'[r] / pivot (src/solver.cu:43, `col == colPivotIndex`).  la_flush_kernel writes rowp' back when
-//     the host wants to look at the tableau.
+//   * row 0 (RHS) is not in the row list; the helpers update it.
+//   * Tiles are handed out by ONE 64-bit atomic word: [ticket count | published row | published column | quiet bit].
+//     The entering variable's row (by the CTA that finishes the cost tournament) and the next pivot column (by the
+//     helpers) are published by adding / or-ing them into that word; the value the atomic returns is the number of
+//     tiles claimed before the publication.  A CTA that claims a tile learns, from the same atomic that gives it the
+//     tile, which publications preceded its claim -- single-location coherence order, no fences.  It then leaves the
+//     published row untouched and holds the published column old; the helpers compute those elements themselves
+//     from the old values.
+//   * Tiles claimed BEFORE a publication are updated in full; the helpers wait for the tile's completion record
+//     (pivot number + "held the column" bit) and read the new values.  Once every helper has classified its rows the
+//     quiet bit stops the record traffic.
+//   * The next pivot column may thus stay stale in the tableau.  It is never read: during the next pivot its raw
+//     values ARE the gathered vector rowp', and the streaming loop overwrites the column with rowp'[r] / pivot
+//     (src/solver.cu:43, `col == colPivotIndex`); rows that update skips (a_pr == 0) get the true entry from the
+//     helpers (stage 0).  la_flush_kernel writes rowp' back when the host wants to look at the tableau.
+//   * Nothing of pivot k+1 is committed by pivot k: basis, trace, hash, counters and status change only when the last
+//     CTA of a launch leaves (la_finalize + commit), so a pivot budget stops exactly and an unused proposal stays valid.
+//
+// Hand-overs.  Under a saturated memory system a dependent global access costs 2-4 us, so the chain avoids them: each
+// stage issues all its loads at once; helpers hand over through per-helper flags that everybody polls (no "last CTA"
+// stage); stage 2 of the ratio tournament is replayed by every helper; the column publication is an idempotent
+// atomicOr whose return value is each helper's own ticket snapshot; helper h gathers (owner rank) or receives (other
+// ranks, from the owner's helper h) the contiguous slice of the pivot constraint it later compacts into the row list.
 //
 // Row list.  The chain also compacts the rows the next update has to stream into a list (row index + pivot-
 // constraint entry a_pr): every stored row except row 0, or -- skip_zero_rows -- only those with a_pr != 0
