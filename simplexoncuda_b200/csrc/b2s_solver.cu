@@ -521,7 +521,7 @@ struct SolverImpl final : SolverBase {
     {
         int mode = opt.lookahead;
         if (const char* e = getenv("B2S_LOOKAHEAD")) mode = atoi(e);
-        if (mode == 0 || use_persistent() || variant_index() != 8) return false;
+        if (mode == 0 || use_persistent() || variant_index() != 8 || !tile_rec) return false;
         if (world > 1 && !p2p) return false;
         // auto: the chain takes ~30 us even on an idle memory system (profiles/r02_lookahead.md); on one GPU it only pays once a
         // pivot streams longer than that, i.e. from ~280 MB of stored tableau (measured crossover, r02_loop_mode_sweep).  Sharded
