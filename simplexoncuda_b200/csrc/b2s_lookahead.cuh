@@ -207,6 +207,30 @@ __device__ __forceinline__ LaClaim la_decode(unsigned long long w)
     return c;
 }
 
+// Loads of data other SMs wrote earlier.  Per-launch kernel (COH = false): written by an EARLIER launch, so the read-only
+// path is fine.  Persistent variant (COH = true): several pivots run inside one launch, L1 is never invalidated in between,
+// so everything another SM may have written comes from L2.
+template <bool COH, typename X>
+__device__ __forceinline__ X la_ld(const X* p)
+{
+    return COH ? __ldcg(p) : __ldg(p);
+}
+template <bool COH, typename X>
+__device__ __forceinline__ X la_ldrw(const X* p)   // read-write data of this kernel (the cost vector)
+{
+    return COH ? __ldcg(p) : *p;
+}
+__device__ __forceinline__ long long ld_acquire_s64(const long long* p)
+{
+    long long v;
+    asm volatile("ld.acquire.gpu.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_s64(long long* p, long long v)
+{
+    asm volatile("st.release.gpu.global.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
 struct LaShared {
     unsigned long long next_word;
     int ok;
@@ -256,7 +280,7 @@ __device__ __noinline__ real la_max512(real v, real* smax)
 // on the streaming CTAs leave that row to the helpers) and releases q' (or "optimal") to the helpers.
 // Runs on the CTAs first_cta .. first_cta+ncta-1.
 // ---------------------------------------------------------------------------------------------
-template <typename real>
+template <typename real, bool COH>
 __device__ __noinline__ void la_cost_blocks(const PivotParams<real>& P, LaState* la, Proposal* nxt, unsigned tseq,
                                             const real* rowp, real sc, int first_cta, int ncta, const int* posC, int tile_rows,
                                             TreeSmem<real>& sm, LaShared& sh)
@@ -270,8 +294,8 @@ __device__ __noinline__ void la_cost_blocks(const PivotParams<real>& P, LaState*
         c.k = -1;
         for (long long i = (long long)b * kSelBlock + threadIdx.x; i < Nc; i += (long long)kSelBlock * P.Gc) {
             const long long j = 1 + i;
-            real v = P.cost[j];
-            v = fma_r(sc, __ldg(rowp + stored_row(P, j)), v);  // src/solver.cu:54
+            real v = la_ldrw<COH>(P.cost + j);
+            v = fma_r(sc, la_ld<COH>(rowp + stored_row(P, j)), v);  // src/solver.cu:54
             P.cost[j] = v;
             Cand<real> o;
             o.v = v;
@@ -279,7 +303,7 @@ __device__ __noinline__ void la_cost_blocks(const PivotParams<real>& P, LaState*
             o.k = (rule == kRuleBland) ? (cmp3((double)v, 0.0) < 0 ? (int)i : -1) : (int)i;
             if (beats(rule, o, c)) c = o;
         }
-        if (b == 0 && threadIdx.x == 0) P.cost[0] = fma_r(sc, __ldg(rowp), P.cost[0]);  // objective value
+        if (b == 0 && threadIdx.x == 0) P.cost[0] = fma_r(sc, la_ld<COH>(rowp), la_ldrw<COH>(P.cost));  // objective value
         la_tree512(rule, c, sm);
         if (threadIdx.x == 0) {
             P.cslot_v[b] = c.v;
@@ -305,8 +329,8 @@ __device__ __noinline__ void la_cost_blocks(const PivotParams<real>& P, LaState*
                     // publish the entering variable's row: tiles claimed from now on leave it to the helpers.  Its position in
                     // the running list and its pivot-constraint entry travel with q', so the helpers need no further lookup.
                     const long long rq = stored_row(P, 1 + (long long)w.i);
-                    const int posq = __ldg(posC + rq);
-                    const real aq = __ldg(rowp + rq);
+                    const int posq = la_ld<COH>(posC + rq);
+                    const real aq = la_ld<COH>(rowp + rq);
                     const unsigned long long old = atomicAdd(&la->word, (unsigned long long)(rq + 1) << kTicketBits);
                     nxt->c_row = (unsigned)(old & kTicketMask);
                     nxt->rbq = posq >= 0 ? posq / tile_rows : -1;
@@ -396,7 +420,7 @@ __device__ __noinline__ bool la_wait_many_sys(const unsigned long long* flags, i
     return __syncthreads_and(ok) != 0;
 }
 
-template <typename real, bool LIVE>
+template <typename real, bool LIVE, bool COH>
 __device__ __noinline__ void la_chain(const PivotParams<real>& P, LaState* la, unsigned seq, int h, int H,
                                       const real* rowp, const real* svec, real piv, long long lp, int p_cur, int q_cur,
                                       bool reverse, long long ntiles, TreeSmem<real>& sm, real* smax, LaShared& sh)
@@ -417,7 +441,7 @@ __device__ __noinline__ void la_chain(const PivotParams<real>& P, LaState* la, u
     const int rpp = kSelBlock >> P.log2_tpr;
     const long long tile_rows = (long long)rpp * P.la_u;
     const long long chunk_cols = (long long)(32 / (int)sizeof(real)) << P.log2_tpr;
-    const real a0 = LIVE ? __ldg(rowp) : (real)0;   // rowp[0] = b_p of the running pivot
+    const real a0 = LIVE ? la_ld<COH>(rowp) : (real)0;   // rowp[0] = b_p of the running pivot
     const bool own_cur = LIVE && lp >= 0 && lp < P.m_loc;
     // Helper h owns the contiguous slice [r_lo, r_hi) of stored rows for the pivot-constraint gather and the row list.
     const long long slice = (((P.Rs + H - 1) / H) + kSelBlock - 1) / kSelBlock * kSelBlock;
@@ -430,8 +454,8 @@ __device__ __noinline__ void la_chain(const PivotParams<real>& P, LaState* la, u
 #pragma unroll
     for (int k = 0; k < kLaRB; ++k) {
         const long long r = r_lo + (long long)k * kSelBlock + threadIdx.x;
-        pos0[k] = (LIVE && r < r_hi) ? __ldg(posC + r) : -2;
-        ak0[k] = (LIVE && r < r_hi) ? __ldg(rowp + r) : (real)0;
+        pos0[k] = (LIVE && r < r_hi) ? la_ld<COH>(posC + r) : -2;
+        ak0[k] = (LIVE && r < r_hi) ? la_ld<COH>(rowp + r) : (real)0;
     }
 
     if (LIVE) {
@@ -443,7 +467,7 @@ __device__ __noinline__ void la_chain(const PivotParams<real>& P, LaState* la, u
                 const long long li = (long long)(bl0 + k * H) * kSelBlock + threadIdx.x;
                 const bool ok = bl0 + k * H < P.Gm_loc && li < P.m_loc;
                 x[k] = ok ? __ldcg(P.T + li) : (real)0;
-                sv[k] = ok ? __ldg(svec + li) : (real)0;
+                sv[k] = ok ? la_ld<COH>(svec + li) : (real)0;
             }
 #pragma unroll
             for (int k = 0; k < kLaBB; ++k) {
@@ -459,8 +483,8 @@ __device__ __noinline__ void la_chain(const PivotParams<real>& P, LaState* la, u
                 for (int k = 0; k < kLaRB; ++k) {
                     const long long r = r_lo + ((long long)bt * kLaRB + k) * kSelBlock + threadIdx.x;
                     if (r < r_hi && r != 0) {
-                        const int pos = bt == 0 ? pos0[k] : __ldg(posC + r);
-                        if (pos < 0) P.T[r * P.ld + lp] = bt == 0 ? ak0[k] : __ldg(rowp + r);
+                        const int pos = bt == 0 ? pos0[k] : la_ld<COH>(posC + r);
+                        if (pos < 0) P.T[r * P.ld + lp] = bt == 0 ? ak0[k] : la_ld<COH>(rowp + r);
                     }
                 }
             }
@@ -520,7 +544,7 @@ __device__ __noinline__ void la_chain(const PivotParams<real>& P, LaState* la, u
             const bool ok = bl0 + k * H < P.Gm_loc && li < P.m_loc;
             av[k] = ok ? __ldcg(P.T + rq * P.ld + li) : (real)0;
             bv[k] = ok ? __ldcg(P.T + li) : (real)0;
-            sv[k] = (ok && old_vals[k]) ? __ldg(svec + li) : (real)0;
+            sv[k] = (ok && old_vals[k]) ? la_ld<COH>(svec + li) : (real)0;
         }
 #pragma unroll
         for (int k = 0; k < kLaBB; ++k) {   // (unrolled: av/bv/sv live in registers; the body is a call)
@@ -537,7 +561,7 @@ __device__ __noinline__ void la_chain(const PivotParams<real>& P, LaState* la, u
                 }
                 if (rule == kRuleBland) {
                     const long long gi = P.col0 + li;
-                    bvar = (LIVE && gi == p_cur) ? q_cur : P.base[gi];   // base[p] = q of the running pivot is committed at its end
+                    bvar = (LIVE && gi == p_cur) ? q_cur : la_ld<COH>(P.base + gi);   // base[p] = q of the running pivot is committed at its end
                 }
             }
             Cand<real> c;
@@ -657,7 +681,7 @@ __device__ __noinline__ void la_chain(const PivotParams<real>& P, LaState* la, u
     }
     {
         const int chunk = owner ? (int)(lpn / chunk_cols) : 0;
-        const real sp = (LIVE && owner && !same_col) ? __ldg(svec + lpn) : (real)0;
+        const real sp = (LIVE && owner && !same_col) ? la_ld<COH>(svec + lpn) : (real)0;
         int bad = 0;
         for (int bt = 0; bt < nbatch; ++bt) {
             real v[kLaRB];
@@ -672,7 +696,7 @@ __device__ __noinline__ void la_chain(const PivotParams<real>& P, LaState* la, u
 #pragma unroll
                 for (int k = 0; k < kLaRB; ++k) {
                     const long long r = rb0 + (long long)k * kSelBlock;
-                    v[k] = (r < r_hi) ? la_div(bt == 0 ? ak0[k] : __ldg(rowp + r), piv) : (real)0;   // T'[r][p] = a_pr / pivot (src/solver.cu:43)
+                    v[k] = (r < r_hi) ? la_div(bt == 0 ? ak0[k] : la_ld<COH>(rowp + r), piv) : (real)0;   // T'[r][p] = a_pr / pivot (src/solver.cu:43)
                 }
             } else {
                 int pos[kLaRB];
@@ -681,8 +705,8 @@ __device__ __noinline__ void la_chain(const PivotParams<real>& P, LaState* la, u
 #pragma unroll
                 for (int k = 0; k < kLaRB; ++k) {
                     const long long r = rb0 + (long long)k * kSelBlock;
-                    pos[k] = bt == 0 ? pos0[k] : ((LIVE && r < r_hi) ? __ldg(posC + r) : -2);
-                    ak[k] = bt == 0 ? ak0[k] : ((LIVE && r < r_hi) ? __ldg(rowp + r) : (real)0);
+                    pos[k] = bt == 0 ? pos0[k] : ((LIVE && r < r_hi) ? la_ld<COH>(posC + r) : -2);
+                    ak[k] = bt == 0 ? ak0[k] : ((LIVE && r < r_hi) ? la_ld<COH>(rowp + r) : (real)0);
                     if (!LIVE || r == 0 || r == rq || r >= r_hi) pos[k] = -2;
                 }
                 // -2: final in the tableau (rows 0 and 1+q' were finished by stages 0 / R; quiescent tableau)
@@ -895,8 +919,12 @@ __device__ __forceinline__ int la_finalize(LaState* la, Proposal* nxt, unsigned 
 // update_la_kernel -- see the header of this file.  256-bit accesses, 8 rows in flight per thread, tiles of
 // (512 >> log2_tpr) * 8 list rows x one column chunk, handed out by the ticket word.
 // ---------------------------------------------------------------------------------------------
-template <typename real, int U>
-__global__ void __launch_bounds__(kSelBlock, 1) update_la_kernel(const __grid_constant__ PivotParams<real> P)
+// PERSIST = false: one pivot per launch (the launches of a batch are replayed as a CUDA graph).  PERSIST = true: up to `batch`
+// pivots per cooperative launch; between two pivots the CTA that commits releases the new pivot count and everybody waits
+// for it -- a grid barrier with the commit inside, ~2 us instead of a kernel boundary.  Data written during the launch is
+// then read through L2 only (la_ld<true>, 256-bit ld.global.cg for the tiles).
+template <typename real, int U, bool PERSIST>
+__global__ void __launch_bounds__(kSelBlock, 1) update_la_kernel(const __grid_constant__ PivotParams<real> P, int batch)
 {
     constexpr int VB = 32;
     constexpr int EPT = VB / (int)sizeof(real);
@@ -910,8 +938,11 @@ __global__ void __launch_bounds__(kSelBlock, 1) update_la_kernel(const __grid_co
     // Programmatic dependent launch: this grid may have been scheduled while the previous pivot's grid was draining; nothing
     // may be read before that grid has completed.  Let the next pivot's grid be scheduled behind this one right away -- its
     // CTAs take the SMs as ours leave and wait here.
-    pdl_wait();
-    pdl_trigger();
+    if (!PERSIST) {
+        pdl_wait();
+        pdl_trigger();
+    }
+  for (int it = 0; it < (PERSIST ? batch : 1); ++it) {
     // One round trip for everything the kernel needs to know: the loop state and BOTH proposals are fetched together and
     // the right generation is picked afterwards (a dependent second and third fetch would cost a microsecond each).
     const int status = __ldcg(&st->status);
@@ -929,7 +960,7 @@ __global__ void __launch_bounds__(kSelBlock, 1) update_la_kernel(const __grid_co
         sc2[g] = __ldcg(&la->prop[g].sc);
         piv2[g] = __ldcg(&la->prop[g].piv);
     }
-    if (status != kRunning || pivots >= limit) return;
+    if (status != kRunning || pivots >= limit) return;   // (uniform over the grid: written before the last barrier / launch)
     const unsigned seq = (unsigned)(pivots + 1);
     const int par = (int)(seq & 1u);
     const Proposal* cur = &la->prop[par];
@@ -956,11 +987,11 @@ __global__ void __launch_bounds__(kSelBlock, 1) update_la_kernel(const __grid_co
         const int first = ((int)gridDim.x > H) ? H : 0;
         const int ncta = (int)gridDim.x - first;
         if ((int)blockIdx.x >= first && (int)blockIdx.x - first < P.Gc)
-            la_cost_blocks<real>(P, la, &la->prop[par ^ 1], seq + 1u, rowp, sc_cur, first, ncta,
+            la_cost_blocks<real, PERSIST>(P, la, &la->prop[par ^ 1], seq + 1u, rowp, sc_cur, first, ncta,
                                  P.rowpos + (size_t)par * P.rowp_stride, tile_rows, sm, sh);
     }
     if (helper)
-        la_chain<real, true>(P, la, seq, (int)blockIdx.x, H, rowp, svec, piv_cur, (long long)lp, p, q, reverse,
+        la_chain<real, true, PERSIST>(P, la, seq, (int)blockIdx.x, H, rowp, svec, piv_cur, (long long)lp, p, q, reverse,
                              (long long)ntiles, sm, smax, sh);
 
     // ---- streaming ---------------------------------------------------------------------------------------
@@ -996,8 +1027,8 @@ __global__ void __launch_bounds__(kSelBlock, 1) update_la_kernel(const __grid_co
             const int rb0 = tmap0 / P.nchunks;
             for (int e = threadIdx.x; e < tile_rows; e += kSelBlock) {
                 const int k = rb0 * tile_rows + e;
-                ts.row[0][e] = (k < nlive) ? __ldg(rlist + k) : -1;
-                ts.val[0][e] = (k < nlive) ? __ldg(rval + k) : (real)0;
+                ts.row[0][e] = (k < nlive) ? la_ld<PERSIST>(rlist + k) : -1;
+                ts.val[0][e] = (k < nlive) ? la_ld<PERSIST>(rval + k) : (real)0;
             }
         }
         __syncthreads();
@@ -1022,11 +1053,11 @@ __global__ void __launch_bounds__(kSelBlock, 1) update_la_kernel(const __grid_co
             }
 #pragma unroll
             for (int u = 0; u < U; ++u)
-                if (row[u] >= 0) v[u].p = ld_pack<0>(reinterpret_cast<const Pack<VB>*>(P.T + (long long)row[u] * P.ld + c));
+                if (row[u] >= 0) v[u].p = ld_pack<PERSIST ? 3 : 0>(reinterpret_cast<const Pack<VB>*>(P.T + (long long)row[u] * P.ld + c));
             if (chunk != cur_chunk && c < P.ld) {
                 cur_chunk = chunk;
 #pragma unroll
-                for (int e = 0; e < EPT; ++e) sreg[e] = __ldg(svec + c + e);
+                for (int e = 0; e < EPT; ++e) sreg[e] = la_ld<PERSIST>(svec + c + e);
             }
             if (threadIdx.x < 32) {
                 // warp 0: the record of the previous tile goes out, the next tile's list entries come in
@@ -1039,8 +1070,8 @@ __global__ void __launch_bounds__(kSelBlock, 1) update_la_kernel(const __grid_co
                     const int nrb = ntmap / P.nchunks;
                     for (int e = threadIdx.x; e < tile_rows; e += 32) {
                         const int k = nrb * tile_rows + e;
-                        ts.row[buf ^ 1][e] = (k < nlive) ? __ldg(rlist + k) : -1;
-                        ts.val[buf ^ 1][e] = (k < nlive) ? __ldg(rval + k) : (real)0;
+                        ts.row[buf ^ 1][e] = (k < nlive) ? la_ld<PERSIST>(rlist + k) : -1;
+                        ts.val[buf ^ 1][e] = (k < nlive) ? la_ld<PERSIST>(rval + k) : (real)0;
                     }
                 }
             }
@@ -1087,7 +1118,7 @@ __global__ void __launch_bounds__(kSelBlock, 1) update_la_kernel(const __grid_co
             Proposal* nxt = &la->prop[par ^ 1];
             P.base[p] = q;   // src/solver.cu:105
             if (pivots < P.trace_cap) P.trace[pivots] = make_int2(q, p);
-            unsigned long long hsh = st->hash;
+            unsigned long long hsh = __ldcg(&st->hash);   // (L2: in the persistent variant another SM committed the previous pivot)
             const unsigned int words[2] = {(unsigned)q, (unsigned)p};
 #pragma unroll
             for (int wd = 0; wd < 2; ++wd)
@@ -1099,16 +1130,45 @@ __global__ void __launch_bounds__(kSelBlock, 1) update_la_kernel(const __grid_co
             st->hash = hsh;
             st->q = q;
             st->p = p;
-            st->rows_streamed += (long long)nlive + 1;
+            st->rows_streamed = __ldcg(&st->rows_streamed) + (long long)nlive + 1;
             const int next_status = la_finalize(la, nxt, seq + 1u, H, true);
             st->status = next_status;
-            st->pivots = pivots + 1;
             la->word = 0ull;
             la->tile_done = 0u;
             la->stamps[6] = globaltimer();
-            __threadfence();
+            if (PERSIST) {
+                st_release_s64(&st->pivots, pivots + 1);   // the barrier's release: everything above is visible with it
+            } else {
+                st->pivots = pivots + 1;
+                __threadfence();
+            }
         }
     }
+    if (PERSIST) {
+        // grid barrier: wait until this pivot is committed (bounded: a CTA that never arrives must not hang the GPU)
+        if (threadIdx.x == 0) {
+            const long long t0 = clock64();
+            int ok = 1;
+            while (ld_acquire_s64(&st->pivots) <= pivots) {
+                if (clock64() - t0 > P.wait_cycles) {
+                    ok = 0;
+                    break;
+                }
+            }
+            sh.ok = ok;
+        }
+        __syncthreads();
+        const bool ok = sh.ok != 0;
+        __syncthreads();
+        if (!ok) {
+            if (threadIdx.x == 0) {
+                st->status = kStatusPeerTimeout;
+                __threadfence();
+            }
+            return;
+        }
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1128,7 +1188,7 @@ __global__ void __launch_bounds__(kSelBlock, 1) la_prologue_kernel(const __grid_
     if (status != kRunning || pivots >= limit) return;
     const unsigned seq = (unsigned)pivots;   // the chain prepares pivot seq + 1
     if (__ldcg(&la->prop[(seq + 1u) & 1u].ready_seq) == seq + 1u) return;
-    la_chain<real, false>(P, la, seq, (int)blockIdx.x, (int)gridDim.x, nullptr, nullptr, (real)0, -1, -1, -1, false, 0, sm, smax, sh);
+    la_chain<real, false, false>(P, la, seq, (int)blockIdx.x, (int)gridDim.x, nullptr, nullptr, (real)0, -1, -1, -1, false, 0, sm, smax, sh);
 }
 
 // The prologue's verdicts (unbounded at the first pivot, a silent peer) have no running pivot to ride on.

@@ -158,6 +158,7 @@ struct SolverImpl final : SolverBase {
     int *rowlist = nullptr, *rowpos = nullptr;
     int la_grid = 0;
     int la_u = 8;
+    bool la_persist = false;  // B2S_LA_PERSIST=1
     bool la_pdl = false;  // programmatic dependent launch between consecutive pivots: measured, no gain (profiles/r02_lookahead.md)
     int la_helpers = 0;   // 0 = default: 8 on one GPU (chain hidden anyway), 16 when sharded (the chain is the critical path)
     long long wait_cycles = 4000000000ll;
@@ -287,6 +288,7 @@ struct SolverImpl final : SolverBase {
         CK(cudaMemsetAsync(la, 0, sizeof(LaState), stream));
         if (const char* e = getenv("B2S_LA_U")) la_u = atoi(e) == 4 ? 4 : 8;
         if (const char* e = getenv("B2S_LA_PDL")) la_pdl = atoi(e) != 0;
+        if (const char* e = getenv("B2S_LA_PERSIST")) la_persist = atoi(e) != 0;
         if (const char* e = getenv("B2S_LA_HELPERS")) la_helpers = std::max(1, std::min(kLaMaxHelpers, atoi(e)));
         if (const char* e = getenv("B2S_PEER_TIMEOUT_MS")) wait_cycles = std::max(1ll, atoll(e)) * 2000000ll;  // ~2 GHz
         if (const char* e = getenv("B2S_FAULT_RANK")) fault_rank = atoi(e);
@@ -531,8 +533,11 @@ struct SolverImpl final : SolverBase {
         if (R1 >= (long long)kRowMask - 1 || ld >= (long long)kNoColumn - 1) return false;  // ticket-word fields
         return true;
     }
-    typedef void (*LaFn)(const PivotParams<real>);
-    LaFn la_fn() const { return la_u == 4 ? (LaFn)update_la_kernel<real, 4> : (LaFn)update_la_kernel<real, 8>; }
+    typedef void (*LaFn)(const PivotParams<real>, int);
+    LaFn la_fn() const { return la_u == 4 ? (LaFn)update_la_kernel<real, 4, false> : (LaFn)update_la_kernel<real, 8, false>; }
+    LaFn la_persist_fn() const { return (LaFn)update_la_kernel<real, 8, true>; }
+    // several pivots per cooperative launch of the look-ahead kernel (grid barrier instead of a kernel boundary)
+    bool use_la_persist() const { return la_persist && la_u == 8 && use_lookahead(); }
     typedef void (*LoopFn)(PivotParams<real>, int);
     LoopFn loop_fn() const
     {
@@ -994,7 +999,7 @@ struct SolverImpl final : SolverBase {
     int launch_la()
     {
         if (!la_pdl) {
-            la_fn()<<<la_grid, kSelBlock, 0, stream>>>(P);
+            la_fn()<<<la_grid, kSelBlock, 0, stream>>>(P, 1);
             return B2S_OK;
         }
         return launch_pdl((const void*)la_fn(), (unsigned)la_grid, kSelBlock);
@@ -1012,7 +1017,8 @@ struct SolverImpl final : SolverBase {
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        void* args[] = {&P};
+        int one = 1;
+        void* args[] = {&P, &one};   // (the three-launch kernels take P only: a trailing argument is ignored by the launch)
         CK(cudaLaunchKernelExC(&cfg, fn, args));
         return B2S_OK;
     }
@@ -1054,6 +1060,17 @@ struct SolverImpl final : SolverBase {
 
     int launch_batch(int batch)
     {
+        if (use_la_persist()) {
+            PivotParams<real> Pk = P;
+            int bk = batch;
+            void* args[] = {&Pk, &bk};
+            cudaError_t ce = cudaLaunchCooperativeKernel((const void*)la_persist_fn(), dim3((unsigned)la_grid), dim3(kSelBlock), args, 0, stream);
+            if (ce == cudaSuccess) return B2S_OK;
+            if (ce != cudaErrorCooperativeLaunchTooLarge && ce != cudaErrorLaunchOutOfResources)
+                return fail(B2S_ERR_CUDA, "cooperative launch of the look-ahead kernel: %s", cudaGetErrorString(ce));
+            cudaGetLastError();
+            la_persist = false;   // the SMs cannot host one CTA each right now: one launch per pivot from here on
+        }
         if (use_persistent()) {
             // one cooperative launch runs the whole batch of pivots (b2s_persistent.cuh)
             CK(cudaMemsetAsync(&st->bar_count, 0, sizeof(unsigned), stream));
