@@ -217,3 +217,39 @@ def test_slab_arithmetic():
         sharding.slab(0, 3, 2048)
     with pytest.raises(ValueError):
         sharding.slab(2, 2, 2048)
+
+
+# ---- host-layer bootstrap (b2s_dist_init_host): the all-gather the library calls back into ------------------------------
+def _ag_worker(rank, world, port, q):
+    import ctypes as C
+    sys.path.insert(0, ROOT)
+    from simplexoncuda_b200 import sharding
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ag = sharding.make_host_allgather(dist)
+    ok = True
+    for nbytes in (4, 64, 8 * 1000 + 3):          # a barrier word, a CUDA-IPC handle, a cost vector with an odd length
+        send = (C.c_ubyte * nbytes)(*[(rank * 37 + i) & 0xFF for i in range(nbytes)])
+        recv = (C.c_ubyte * (nbytes * world))()
+        rc = ag(C.addressof(send), C.addressof(recv), nbytes)
+        got = bytes(recv)
+        want = b"".join(bytes((r * 37 + i) & 0xFF for i in range(nbytes)) for r in range(world))
+        ok = ok and rc == 0 and got == want
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+def test_host_allgather_callback_world2():
+    """The b2s_allgather_fn that sharding.init_sharded_solver_host hands to the library: every rank's bytes, in rank order,
+    on every rank (gloo, CPU).  The GPU side of the same bootstrap is tests/test_sharded_same_gpu.py."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_ag_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)]
