@@ -157,7 +157,8 @@ struct SolverImpl final : SolverBase {
     real *col2 = nullptr, *s2 = nullptr, *rowp2 = nullptr, *rowval = nullptr;
     int *rowlist = nullptr, *rowpos = nullptr;
     int la_grid = 0;
-    int la_u = 8;
+    int la_u = 8;          // 256-bit loads in flight per streaming thread (set per problem in fill_params)
+    int la_u_env = 0;      // B2S_LA_U: 0 = choose
     bool la_persist = false;  // B2S_LA_PERSIST=1
     bool la_pdl = false;  // programmatic dependent launch between consecutive pivots: measured, no gain (profiles/r02_lookahead.md)
     int la_helpers = 0;   // 0 = default: 8 on one GPU (chain hidden anyway), 16 when sharded (the chain is the critical path)
@@ -286,7 +287,7 @@ struct SolverImpl final : SolverBase {
         CK(cudaMemsetAsync(st, 0, sizeof(DevState), stream));  // `stream` is non-blocking: never mix in legacy-stream calls
         CK(cudaMalloc(&la, sizeof(LaState)));
         CK(cudaMemsetAsync(la, 0, sizeof(LaState), stream));
-        if (const char* e = getenv("B2S_LA_U")) la_u = atoi(e) == 4 ? 4 : 8;
+        if (const char* e = getenv("B2S_LA_U")) la_u_env = atoi(e) == 4 ? 4 : 8;
         if (const char* e = getenv("B2S_LA_PDL")) la_pdl = atoi(e) != 0;
         if (const char* e = getenv("B2S_LA_PERSIST")) la_persist = atoi(e) != 0;
         if (const char* e = getenv("B2S_LA_HELPERS")) la_helpers = std::max(1, std::min(kLaMaxHelpers, atoi(e)));
@@ -646,6 +647,10 @@ struct SolverImpl final : SolverBase {
         }
         // look-ahead kernel: same tile geometry as variant 8; tiles are cut from the per-pivot row list, so size by the maximum
         {
+            // Sharded slabs that stream in less time than the chain takes (< ~350 MB): half the bytes in flight per thread halves
+            // the queueing delay every dependent access of the chain sees, and the lost streaming bandwidth is hidden
+            // (N=4: 57.0 vs 61.4 us per pivot, N=8: 50.4 vs 52.2; one GPU / large slabs: 8 -- profiles/r02_lookahead.md).
+            la_u = la_u_env ? la_u_env : ((world > 1 && (double)Rs * (double)ld * sizeof(real) < 350e6) ? 4 : 8);
             const long long rows_tile8 = (long long)rpp * la_u;
             const long long max_tiles = ((R1 + rows_tile8 - 1) / rows_tile8 + 1) * P.nchunks;
             P.la_u = la_u;

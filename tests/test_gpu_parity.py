@@ -195,6 +195,18 @@ def test_lookahead_helper_counts(S, helpers, monkeypatch):
     check_solve(S, A, b, c, max_pivots=100000, persistent=False, lookahead=True)
 
 
+@pytest.mark.parametrize("env", [{"B2S_LA_U": "4"}, {"B2S_LA_PERSIST": "1"}, {"B2S_LA_PDL": "1"}])
+def test_lookahead_kernel_variants(S, env, monkeypatch):
+    """The look-ahead kernel's tuning variants -- 4 instead of 8 loads in flight per thread (what small sharded slabs use),
+    several pivots per cooperative launch, programmatic dependent launch -- give the same pivots as the oracle."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    A, b, c = O.generate(300, 2600, O.seed_triplet(21, 1), 1, 100)
+    check_solve(S, A, b, c, persistent=False, lookahead=True, max_pivots=400)
+    A, b, c = O.generate(90, 70, O.seed_triplet(5, 0), -100, 100)
+    check_solve(S, A, b, c, max_pivots=100000, persistent=False, lookahead=True)
+
+
 @pytest.mark.parametrize("chunk", [2, 7])
 def test_lookahead_chunked_iterate_bit_exact(S, chunk):
     """iterate(k) in chunks: the proposal prepared by the last kernel of one call is consumed by the first kernel of the next,
