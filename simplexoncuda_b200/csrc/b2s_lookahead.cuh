@@ -68,6 +68,8 @@ constexpr unsigned kNoColumn = 0x7ffffeu;                         // "no column 
 constexpr unsigned long long kColMask = (1ull << 23) - 1ull;
 constexpr unsigned long long kQuietBit = 1ull << 63;              // the helpers are done classifying: stop writing tile records
 constexpr unsigned kRecHeld = 0x80000000u;                        // tile record: the claimer held the published column old
+constexpr unsigned kRecRowHeld = 0x40000000u;                     // tile record: the claimer left the published row alone
+constexpr unsigned kRecSeqMask = 0x3fffffffu;                     // tile record: pivot number (mod 2^30)
 
 // The complete selection of one pivot.  Two generations, indexed by the parity of the pivot number.
 struct Proposal {
@@ -81,10 +83,7 @@ struct Proposal {
     unsigned p_seq;   // == pivot number once p is valid (or status_next == kUnbounded)
     unsigned rowp_seq;   // one GPU: == pivot number once rowp' is complete (sharded: the arena's flag_rowp)
     unsigned ready_seq;  // == pivot number once everything is in place: the pivot may execute
-    unsigned c_row;   // tiles claimed before the row publication
-    int rbq;          // row block of the running update's list that holds row 1+q' (-1: none)
-    double aq;        // rowp[1+q'] of the running pivot
-    unsigned pad1, pad2;
+    unsigned pad1, pad2, pad3, pad4;
     long long nz;     // length of the row list: rows (other than row 0) the update of this pivot streams
 };
 
@@ -98,6 +97,7 @@ struct LaState {
     int cnt[kLaMaxHelpers];
     unsigned slot_seq[kLaMaxHelpers]; // one GPU: helper h has written its ratio-test block winners for pivot slot_seq[h]
     unsigned done_seq[kLaMaxHelpers]; // helper h has finished the chain for pivot done_seq[h]
+    unsigned cost_seq[kMaxSlots];     // cost stage-1 block b has written its winner for pivot cost_seq[b]
     unsigned long long stamps[8];  // %globaltimer at the chain's milestones of the last pivot (profiling)
 };
 
@@ -165,7 +165,7 @@ __device__ __noinline__ unsigned la_poll_rec(const unsigned* rec, unsigned seq, 
 {
     const long long t0 = clock64();
     unsigned v;
-    while (((v = ld_acquire_u32(rec)) & 0x7fffffffu) != seq) {
+    while (((v = ld_acquire_u32(rec)) & kRecSeqMask) != (seq & kRecSeqMask)) {
         if (clock64() - t0 > cycles) break;
     }
     return v;
@@ -275,15 +275,12 @@ __device__ __noinline__ real la_max512(real v, real* smax)
 
 // ---------------------------------------------------------------------------------------------
 // Stage "cost": cost update of the running pivot (src/solver.cu:48-56) + entering tournament of the next
-// (src/reduction.cu:51-104 over costsVector+1).  Block b plays reference stage-1 block b; the CTA that
-// draws the last ticket plays stage 2, publishes the entering variable's row into the ticket word (from then
-// on the streaming CTAs leave that row to the helpers) and releases q' (or "optimal") to the helpers.
-// Runs on the CTAs first_cta .. first_cta+ncta-1.
+// (src/reduction.cu:51-104 over costsVector+1).  Block b plays reference stage-1 block b and raises flag b; stage 2 is
+// replayed by every helper (la_chain, stage Q).  Runs on the CTAs first_cta .. first_cta+ncta-1.
 // ---------------------------------------------------------------------------------------------
 template <typename real, bool COH>
-__device__ __noinline__ void la_cost_blocks(const PivotParams<real>& P, LaState* la, Proposal* nxt, unsigned tseq,
-                                            const real* rowp, real sc, int first_cta, int ncta, const int* posC, int tile_rows,
-                                            TreeSmem<real>& sm, LaShared& sh)
+__device__ __noinline__ void la_cost_blocks(const PivotParams<real>& P, LaState* la, unsigned tseq, const real* rowp, real sc,
+                                            int first_cta, int ncta, TreeSmem<real>& sm)
 {
     const long long Nc = P.Rc - 1;
     const int rule = P.rule;
@@ -306,42 +303,13 @@ __device__ __noinline__ void la_cost_blocks(const PivotParams<real>& P, LaState*
         if (b == 0 && threadIdx.x == 0) P.cost[0] = fma_r(sc, la_ld<COH>(rowp), la_ldrw<COH>(P.cost));  // objective value
         la_tree512(rule, c, sm);
         if (threadIdx.x == 0) {
+            // block winner + its flag: every helper polls the flags and replays stage 2 itself (no "last CTA" stage)
             P.cslot_v[b] = c.v;
             P.cslot_i[b] = c.i;
             P.cslot_k[b] = c.k;
-            __threadfence();
-            const unsigned t = atomicAdd(&la->ticket_cost, 1u);
-            sh.flag = (t == (unsigned)P.Gc - 1u);
+            st_release_u32(&la->cost_seq[b], tseq);
         }
         __syncthreads();
-        const bool last = sh.flag != 0;
-        __syncthreads();
-        if (last) {
-            __threadfence();
-            Cand<real> w;
-            la_stage2(rule, P.cslot_v, P.cslot_i, P.cslot_k, P.Gc, w, sm);   // (one block: its own winner, just written)
-            if (threadIdx.x == 0) {
-                const bool go = w.i >= 0 && cmp3((double)w.v, 0.0) < 0;   // src/solver.cu:87-88
-                nxt->q = w.i;
-                nxt->cq = (double)w.v;
-                nxt->status_next = go ? kRunning : kFeasible;
-                if (go) {
-                    // publish the entering variable's row: tiles claimed from now on leave it to the helpers.  Its position in
-                    // the running list and its pivot-constraint entry travel with q', so the helpers need no further lookup.
-                    const long long rq = stored_row(P, 1 + (long long)w.i);
-                    const int posq = la_ld<COH>(posC + rq);
-                    const real aq = la_ld<COH>(rowp + rq);
-                    const unsigned long long old = atomicAdd(&la->word, (unsigned long long)(rq + 1) << kTicketBits);
-                    nxt->c_row = (unsigned)(old & kTicketMask);
-                    nxt->rbq = posq >= 0 ? posq / tile_rows : -1;
-                    nxt->aq = (double)aq;
-                } else {
-                    atomicAdd(&la->word, (unsigned long long)kNoColumn << kColShift);   // phase over: no column will follow
-                }
-                la->ticket_cost = 0;
-                st_release_u32(&nxt->q_seq, tseq);
-            }
-        }
     }
 }
 
@@ -412,6 +380,33 @@ __device__ __noinline__ bool la_wait_many_u32(const unsigned* flags, int count, 
         }
     }
     return __syncthreads_and(ok) != 0;
+}
+// The same for any number of flags (each thread polls flags tid, tid + 512, ...).
+__device__ __noinline__ bool la_wait_all_u32(const unsigned* flags, int count, unsigned want, long long cycles)
+{
+    int ok = 1;
+    const long long t0 = clock64();
+    for (int i = threadIdx.x; i < count && ok; i += kSelBlock) {
+        while (ld_acquire_u32(flags + i) != want) {
+            if (clock64() - t0 > cycles) {
+                ok = 0;
+                break;
+            }
+        }
+    }
+    return __syncthreads_and(ok) != 0;
+}
+// Block-uniform bounded wait for a tile's completion record; returns the record (0 on timeout).
+__device__ __noinline__ unsigned la_wait_rec(const unsigned* rec, unsigned seq, long long cycles, LaShared& sh)
+{
+    if (threadIdx.x == 0) {
+        const unsigned v = la_poll_rec(rec, seq, cycles);
+        sh.i1 = (int)(((v & kRecSeqMask) == (seq & kRecSeqMask)) ? v : 0u);
+    }
+    __syncthreads();
+    const unsigned v = (unsigned)sh.i1;
+    __syncthreads();
+    return v;
 }
 __device__ __noinline__ bool la_wait_many_sys(const unsigned long long* flags, int count, unsigned long long want, long long cycles)
 {
@@ -490,27 +485,63 @@ __device__ __noinline__ void la_chain(const PivotParams<real>& P, LaState* la, u
             }
         }
         if (h == 0 && threadIdx.x == 0) la->stamps[1] = globaltimer();
-        // ---- stage Q: the entering variable of the next pivot (the cost CTAs have published its row already) ----
-        if (!la_wait_u32(&nxt->q_seq, tseq, cyc, &sh.ok)) {
-            if (h == 0 && threadIdx.x == 0) {
-                nxt->status_next = kStatusPeerTimeout;
-                atomicAdd(&la->word, (unsigned long long)kNoColumn << kColShift);
+        // ---- stage Q: every helper replays stage 2 of the entering tournament over the cost CTAs' block winners ----------
+        if (!la_wait_all_u32(la->cost_seq, P.Gc, tseq, cyc)) {
+            if (threadIdx.x == 0) atomicOr(&la->word, (unsigned long long)kNoColumn << kColShift);
+            return;   // (q_seq stays behind: la_finalize reports the silent stage)
+        }
+    }
+    int qn;
+    real cqn;
+    long long c_row = 0, rbq = -1;   // rbq: row block of the running list that holds row 1+q'; -1: no tile touches it
+    real aq = (real)0;               // rowp[1+q'] of the running pivot
+    if (LIVE) {
+        Cand<real> wq;
+        la_stage2(rule, P.cslot_v, P.cslot_i, P.cslot_k, P.Gc, wq, sm);
+        if (threadIdx.x == 0) {
+            sh.i0 = wq.i;
+            sh.d0 = (double)wq.v;
+        }
+        __syncthreads();
+        qn = sh.i0;
+        cqn = (real)sh.d0;
+        __syncthreads();
+        const bool go = qn >= 0 && cmp3((double)cqn, 0.0) < 0;   // src/solver.cu:87-88
+        if (h == 0 && threadIdx.x == 0) {
+            nxt->q = qn;
+            nxt->cq = (double)cqn;
+            nxt->status_next = go ? kRunning : kFeasible;
+        }
+        if (!go) {   // optimal after this pivot: nothing to prepare, no column will be published
+            if (threadIdx.x == 0) {
+                atomicOr(&la->word, (unsigned long long)kNoColumn << kColShift);
+                if (h == 0) st_release_u32(&nxt->q_seq, tseq);
             }
             return;
         }
-    } else if (h == 0 && threadIdx.x == 0) {
-        nxt->q = __ldcg(&st->q);
-        nxt->cq = __ldcg(&st->cq);
-        nxt->status_next = kRunning;
+        // Publish the entering variable's row: tiles claimed from now on leave it to the helpers.  Every helper ORs the same
+        // field in and keeps the ticket count ITS atomic returned (as for the column below); meanwhile the two lookups fly.
+        const long long rq0 = stored_row(P, 1 + (long long)qn);
+        const int posq = la_ld<COH>(posC + rq0);
+        aq = la_ld<COH>(rowp + rq0);
+        if (threadIdx.x == 0) {
+            const unsigned long long old = atomicOr(&la->word, (unsigned long long)(rq0 + 1) << kTicketBits);
+            sh.next_word = old & kTicketMask;
+            if (h == 0) st_release_u32(&nxt->q_seq, tseq);
+        }
+        __syncthreads();
+        c_row = (long long)sh.next_word;
+        __syncthreads();
+        if (posq >= 0) rbq = posq / tile_rows;
+    } else {
+        if (h == 0 && threadIdx.x == 0) {
+            nxt->q = __ldcg(&st->q);
+            nxt->cq = __ldcg(&st->cq);
+            nxt->status_next = kRunning;
+        }
+        qn = __ldcg(&st->q);
+        cqn = (real)__ldcg(&st->cq);
     }
-    // everything the cost CTAs left for us, fetched in one go
-    const int sn = LIVE ? __ldcg(&nxt->status_next) : kRunning;
-    const int qn = LIVE ? __ldcg(&nxt->q) : __ldcg(&st->q);
-    const real cqn = (real)(LIVE ? __ldcg(&nxt->cq) : __ldcg(&st->cq));
-    const long long c_row = LIVE ? (long long)__ldcg(&nxt->c_row) : 0;
-    const long long rbq = LIVE ? (long long)__ldcg(&nxt->rbq) : -1;   // -1: no tile of the running update touches row 1+q'
-    const real aq = LIVE ? (real)__ldcg(&nxt->aq) : (real)0;          // rowp[1+q'] of the running pivot
-    if (sn != kRunning) return;   // optimal after this pivot: nothing to prepare
     const long long rq = stored_row(P, 1 + (long long)qn);
     if (h == 0 && threadIdx.x == 0) la->stamps[2] = globaltimer();
 
@@ -528,12 +559,14 @@ __device__ __noinline__ void la_chain(const PivotParams<real>& P, LaState* la, u
                     const int chunk = (int)(((long long)bl * kSelBlock) / chunk_cols);
                     const long long tmap = rbq * P.nchunks + chunk;
                     const long long t = reverse ? (ntiles - 1 - tmap) : tmap;
-                    old_vals[k] = t >= c_row + base;  // claimed after the publication: the claimer leaves row rq alone
-                    if (!old_vals[k]) {               // claimed before: wait until that tile is complete, then read the new values
-                        if (!la_wait_u32(P.tile_rec + tmap, seq, cyc, &sh.ok)) {
+                    old_vals[k] = t >= c_row + base;  // claimed after my snapshot: the claimer certainly leaves row rq alone
+                    if (!old_vals[k]) {               // claimed before: wait until that tile is complete; its record says what it did
+                        const unsigned rec = la_wait_rec(P.tile_rec + tmap, seq, cyc, sh);
+                        if (rec == 0u) {
                             if (threadIdx.x == 0) nxt->status_next = kStatusPeerTimeout;
                             return;
                         }
+                        old_vals[k] = (rec & kRecRowHeld) != 0u;
                     }
                 }
             }
@@ -729,10 +762,10 @@ __device__ __noinline__ void la_chain(const PivotParams<real>& P, LaState* la, u
 #pragma unroll
                 for (int k = 0; k < kLaRB; ++k) {
                     if (pos[k] >= 0) {
-                        if ((rec[k] & ~kRecHeld) != seq) {
+                        if ((rec[k] & kRecSeqMask) != (seq & kRecSeqMask)) {
                             const long long tmap = (pos[k] / tile_rows) * P.nchunks + chunk;
                             rec[k] = la_poll_rec(P.tile_rec + tmap, seq, cyc);
-                            if ((rec[k] & ~kRecHeld) != seq) bad = 1;
+                            if ((rec[k] & kRecSeqMask) != (seq & kRecSeqMask)) bad = 1;
                         }
                         pos[k] = (rec[k] & kRecHeld) ? -1 : -2;
                     }
@@ -987,8 +1020,7 @@ __global__ void __launch_bounds__(kSelBlock, 1) update_la_kernel(const __grid_co
         const int first = ((int)gridDim.x > H) ? H : 0;
         const int ncta = (int)gridDim.x - first;
         if ((int)blockIdx.x >= first && (int)blockIdx.x - first < P.Gc)
-            la_cost_blocks<real, PERSIST>(P, la, &la->prop[par ^ 1], seq + 1u, rowp, sc_cur, first, ncta,
-                                 P.rowpos + (size_t)par * P.rowp_stride, tile_rows, sm, sh);
+            la_cost_blocks<real, PERSIST>(P, la, seq + 1u, rowp, sc_cur, first, ncta, sm);
     }
     if (helper)
         la_chain<real, true, PERSIST>(P, la, seq, (int)blockIdx.x, H, rowp, svec, piv_cur, (long long)lp, p, q, reverse,
@@ -1033,7 +1065,7 @@ __global__ void __launch_bounds__(kSelBlock, 1) update_la_kernel(const __grid_co
         }
         __syncthreads();
         int rec_pending = -1;   // thread 0: tile whose completion record is still to be written
-        unsigned rec_value = seq;
+        unsigned rec_value = seq & kRecSeqMask;
         int cur_chunk = -1;
         real sreg[EPT];
         while (tile < ntiles) {
@@ -1097,7 +1129,7 @@ __global__ void __launch_bounds__(kSelBlock, 1) update_la_kernel(const __grid_co
             }
             // the record says whether this tile held the published column old; once the helpers are done nobody reads records
             rec_pending = want_rec ? tmap : -1;
-            rec_value = seq | (skip_col >= 0 ? kRecHeld : 0u);
+            rec_value = (seq & kRecSeqMask) | (skip_col >= 0 ? kRecHeld : 0u) | (skip_row >= 0 ? kRecRowHeld : 0u);
             __syncthreads();
             buf ^= 1;
             const LaClaim cl = la_decode(ts.word[buf]);
