@@ -394,6 +394,8 @@ def run_b2s(a):
         launches = a.steps * ((P + batch - 1) // batch + 1)
     else:
         launches = launches_per_pivot * pivots
+        if launches_per_pivot == 1:   # look-ahead kernel: + prologue (2) and column write-back (1) per iterate() call
+            launches += 3 * a.steps
     s.close()
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,

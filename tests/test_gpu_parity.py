@@ -227,6 +227,30 @@ def test_lookahead_chunked_iterate_bit_exact(S, chunk):
         assert same(qp, o.trace()) and h == o.hash()
 
 
+@pytest.mark.parametrize("variant", [8, 0])
+def test_per_launch_kernels_after_the_loop_kernel(S, variant):
+    """The cooperative loop kernel leaves the update kernel's tile-ticket counter where its last pivot stopped; per-launch
+    kernels that follow it (b2s_profile_pivots, the cooperative-launch fallback) must find it re-armed, and must tile the
+    tableau with the geometry of the kernel that actually runs (round-1 advisory).  1400 x 1400: more tiles than CTAs."""
+    A, b, c = O.generate(1400, 1400, O.seed_triplet(17, 1), 1, 100)
+    o = O.Oracle(A, b, c, threads=4)
+    with S.Solver(persistent=True, update_variant=variant) as s:
+        s.load(A, b, c)
+        s.build_phase1(); o.build_phase1()
+        s.price_out(); o.priceout()
+        s.select_entering()
+        st, done = s.iterate(5)
+        assert done == 5 and o.iterate(5) == O.CONTINUE
+        prof = s.profile_pivots(3)
+        assert prof["pivots"] == 3 and o.iterate(3) == O.CONTINUE
+        assert same(s.tableau(), o.tableau()) and same(s.costs(), o.costs()) and same(s.basis(), o.basis())
+        st, done = s.iterate(4)
+        assert done == 4 and o.iterate(4) == O.CONTINUE
+        assert same(s.tableau(), o.tableau())
+        qp, cnt, h = s.trace()
+        assert same(qp, o.trace()) and h == o.hash()
+
+
 # ---- published golden vectors at sizes the oracle needs minutes for --------------------------------
 def _grid(max_cons):
     seen = set()
