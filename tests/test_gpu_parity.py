@@ -58,10 +58,19 @@ def test_generator_matches_oracle(S, n, m, lo, hi):
 
 
 # ---- stepping parity: every intermediate state -----------------------------------------------------
-@pytest.mark.parametrize("loop", ["persistent", "lookahead", "launches", "lookahead-noskip"])
-@pytest.mark.parametrize("fold", [True, False])
-@pytest.mark.parametrize("n,m,lo,hi,seed", [(24, 16, -100, 100, 3), (64, 64, 1, 100, 5), (100, 130, -100, 100, 9),
-                                            (600, 520, 1, 100, 11), (300, 2500, 1, 100, 13)])
+def _stepping_cases():
+    small = [(24, 16, -100, 100, 3), (64, 64, 1, 100, 5), (100, 130, -100, 100, 9), (600, 520, 1, 100, 11)]
+    for loop in ("persistent", "lookahead", "launches", "lookahead-noskip"):
+        for fold in (True, False):
+            for case in small:
+                yield (loop, fold) + case
+    # two column chunks per tableau row (m = 2500 -> ld = 2560): the multi-chunk tile geometry, per-launch loop bodies only
+    # (every step copies a 106 MB tableau back, so this size is not multiplied by all modes)
+    for loop, fold in (("lookahead", True), ("launches", True), ("lookahead-noskip", False)):
+        yield (loop, fold, 300, 2500, 1, 100, 13)
+
+
+@pytest.mark.parametrize("loop,fold,n,m,lo,hi,seed", list(_stepping_cases()))
 def test_stepping_bit_exact(S, loop, fold, n, m, lo, hi, seed):
     A, b, c = O.generate(n, m, O.seed_triplet(seed, 0), lo, hi)
     o = O.Oracle(A, b, c)
