@@ -64,10 +64,10 @@ def _stepping_cases():
         for fold in (True, False):
             for case in small:
                 yield (loop, fold) + case
-    # two column chunks per tableau row (m = 2500 -> ld = 2560): the multi-chunk tile geometry, per-launch loop bodies only
-    # (every step copies a 106 MB tableau back, so this size is not multiplied by all modes)
-    for loop, fold in (("lookahead", True), ("launches", True), ("lookahead-noskip", False)):
-        yield (loop, fold, 300, 2500, 1, 100, 13)
+    # two column chunks per tableau row (m = 2500 -> ld = 2560): the multi-chunk tile geometry of the look-ahead kernel, every
+    # intermediate tableau compared (each step copies a 106 MB tableau back, so this size is not multiplied by all modes)
+    # (30 s per case: one is enough; the three-launch body meets multi-chunk rows in the published grid, m >= 4096)
+    yield ("lookahead", True, 300, 2500, 1, 100, 13)
 
 
 @pytest.mark.parametrize("loop,fold,n,m,lo,hi,seed", list(_stepping_cases()))
