@@ -337,6 +337,19 @@ def test_fp32_objective_close_to_fp64_oracle(S, n, m, seed):
     assert abs(float(c @ r["x"]) - r["objective"]) <= 1e-9 * abs(r["objective"])
 
 
+def test_fp32_loop_bodies_agree(S):
+    """fp32 has no oracle to be bit-compared with, but the loop bodies must agree with each other bit for bit: same
+    arithmetic, same trees -- look-ahead kernel (used automatically from 280 MB on), three launches, loop kernel."""
+    A, b, c = O.generate(300, 2600, O.seed_triplet(21, 1), 1, 100)
+    got = []
+    for opts in (dict(persistent=False, lookahead=True), dict(persistent=False, lookahead=False), dict(persistent=True)):
+        with S.Solver(dtype=S.F32, max_pivots=600, fp64_polish=False, **opts) as s:
+            s.load(A, b, c)
+            r = s.solve()
+            got.append((r["status"], int(r["stats"].trace_hash), r["stats"].pivots_phase1))
+    assert got[0] == got[1] == got[2], got
+
+
 def test_fp32_without_polish_is_the_plain_fp32_tableau(S):
     """fp64_polish=False reports the fp32 tableau's own objective: close for a small LP, visibly off for a larger one."""
     A, b, c = O.generate(64, 64, O.seed_triplet(3, 1), 1, 100)
