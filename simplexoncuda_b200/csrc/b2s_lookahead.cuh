@@ -22,14 +22,15 @@
 // Hazard protocol (the streaming CTAs overwrite the tableau in place while the helpers read it):
 //   * row 0 (RHS) is not in the row list; the helpers update it.
 //   * Tiles are handed out by ONE 64-bit atomic word: [ticket count | published row | published column | quiet bit].
-//     The entering variable's row (by the CTA that finishes the cost tournament) and the next pivot column (by the
-//     helpers) are published by adding / or-ing them into that word; the value the atomic returns is the number of
-//     tiles claimed before the publication.  A CTA that claims a tile learns, from the same atomic that gives it the
+//     The entering variable's row and the next pivot column are published by the helpers by or-ing them into that
+//     word (every helper ors the same field in -- idempotent); the value the atomic returns is the number of tiles
+//     claimed before that helper's publication.  A CTA that claims a tile learns, from the same atomic that gives it the
 //     tile, which publications preceded its claim -- single-location coherence order, no fences.  It then leaves the
 //     published row untouched and holds the published column old; the helpers compute those elements themselves
 //     from the old values.
-//   * Tiles claimed BEFORE a publication are updated in full; the helpers wait for the tile's completion record
-//     (pivot number + "held the column" bit) and read the new values.  Once every helper has classified its rows the
+//   * Tiles claimed before a helper's publication may or may not have seen an earlier helper's: the helper waits for
+//     the tile's completion record (pivot number + "left the row alone" / "held the column" bits) and reads the new
+//     values or applies the update itself accordingly.  Once every helper has classified its rows the
 //     quiet bit stops the record traffic.
 //   * The next pivot column may thus stay stale in the tableau.  It is never read: during the next pivot its raw
 //     values ARE the gathered vector rowp', and the streaming loop overwrites the column with rowp'[r] / pivot
@@ -39,8 +40,8 @@
 //     CTA of a launch leaves (la_finalize + commit), so a pivot budget stops exactly and an unused proposal stays valid.
 //
 // Hand-overs.  Under a saturated memory system a dependent global access costs 2-4 us, so the chain avoids them: each
-// stage issues all its loads at once; helpers hand over through per-helper flags that everybody polls (no "last CTA"
-// stage); stage 2 of the ratio tournament is replayed by every helper; the column publication is an idempotent
+// stage issues all its loads at once; the cost CTAs and the helpers hand over through per-block / per-helper flags that
+// everybody polls (no "last CTA" stage); stage 2 of both tournaments is replayed by every helper; the column publication is an idempotent
 // atomicOr whose return value is each helper's own ticket snapshot; helper h gathers (owner rank) or receives (other
 // ranks, from the owner's helper h) the contiguous slice of the pivot constraint it later compacts into the row list.
 //
