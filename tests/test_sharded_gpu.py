@@ -16,6 +16,15 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+def _free_port():
+    import socket
+    sock = socket.socket()
+    sock.bind(("127.0.0.1", 0))
+    port = sock.getsockname()[1]
+    sock.close()
+    return port
+
+
 def _ngpus():
     try:
         import torch
@@ -46,7 +55,7 @@ def test_sharded_solves_match_oracle(world, mode):
              dict(n=1024, m=1024 * world // 2, seed=103424, flavour=1, lo=1, hi=100),
              dict(n=200, m=512 * world, seed=9, flavour=0, lo=1, hi=100, load="host")]
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
-           "--master-addr", "127.0.0.1", "--master-port", "29713", os.path.join(ROOT, "tests", "sharded_worker.py"),
+           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "sharded_worker.py"),
            json.dumps(cases)]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=1200, env=env)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
